@@ -1,0 +1,183 @@
+/*
+ * rcbevdet_b200 -- C ABI of the B200-native (sm_100a) camera->BEV pooling path.
+ *
+ * This is the drop-in boundary.  Every entry point is `extern "C"`, takes plain device
+ * pointers (what torch's `tensor.data_ptr()` returns), sizes and a CUDA stream; there are
+ * no torch types, no globals and no allocation inside (the caller owns every buffer,
+ * workspace included).  All calls are re-entrant and asynchronous on `stream`; they set
+ * the CUDA device from the `device` argument themselves, so they can be called from the
+ * autograd engine's worker thread (the reference relies on OptionalCUDAGuard for that:
+ * mmdet3d/ops/bev_pool_v2/src/bev_pool.cpp:42,88).
+ *
+ * Return value: 0 on success, a negative RCB_ERR_* for argument errors, or a positive
+ * `cudaError_t`.  (The reference's entry points are `void` and unchecked.)
+ *
+ * Which reference interface each entry point replaces is cited on the declaration.
+ */
+#ifndef RCBEVDET_B200_H_
+#define RCBEVDET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *rcb_stream_t; /* == cudaStream_t */
+
+#define RCB_OK 0
+#define RCB_ERR_ARG (-1)         /* null pointer / negative size / inconsistent shape  */
+#define RCB_ERR_WORKSPACE (-2)   /* workspace too small                                */
+#define RCB_ERR_UNSUPPORTED (-3) /* size outside the supported envelope */
+#define RCB_ERR_ALIGN (-4)       /* pointer not aligned as required                    */
+
+#define RCB_DTYPE_F32 0
+#define RCB_DTYPE_BF16 1
+#define RCB_DTYPE_F16 2
+
+/* Output / gradient layouts of the pooled BEV tensor */
+#define RCB_LAYOUT_CELLS_C 0 /* (B*Z*Y*X, C) channels last: what bev_pool_v2_forward writes   */
+#define RCB_LAYOUT_B_C_CELLS 1 /* (B, C, Z*Y*X): what bev_pool_v2() returns (bev_pool.py:91)  */
+
+/* plan flags (rcb_pool_desc.flags, produced by rcb_pool_validate or implied by
+ * rcb_voxel_pooling_prepare_v2) */
+#define RCB_PLAN_RANGES_OK 1      /* every rank is inside its tensor                                   */
+#define RCB_PLAN_INTERVALS_OK 2   /* intervals tile [0, n_points) contiguously, lengths > 0           */
+#define RCB_PLAN_SORTED_CELLS 4   /* interval cells strictly increasing -> zero-filling tile kernel    */
+#define RCB_PLAN_STRUCTURED 8     /* ranks_depth unique and ranks_feat == pixel_of(ranks_depth)        */
+#define RCB_PLAN_ALL 15
+
+int rcb_version(void);
+const char *rcb_error_string(int code);
+/* sm count, L2 bytes, compute capability of `device` (host query, no kernel). */
+int rcb_device_info(int device, int *sm_count, int *l2_bytes, int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Row P -- LSSViewTransformer.voxel_pooling_prepare_v2
+ *          (mmdet3d/models/necks/view_transformer.py:207-265)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int B, N, D, H, W;  /* coor is (B, N, D, H, W, 3) float32 contiguous                          */
+  float lower[3];     /* self.grid_lower_bound (x, y, z)  view_transformer.py:80                 */
+  float interval[3];  /* self.grid_interval                view_transformer.py:81                 */
+  float size[3];      /* self.grid_size (must be integral) view_transformer.py:82-83              */
+} rcb_prepare_desc;
+
+size_t rcb_prepare_workspace_bytes(const rcb_prepare_desc *d);
+
+/*
+ * Outputs (all int32, device):
+ *   ranks_bev / ranks_depth / ranks_feat : capacity P = B*N*D*H*W, first n_kept valid, sorted
+ *       by ranks_bev with ascending ranks_depth inside a cell (the stable order).
+ *   interval_starts / interval_lengths   : capacity min(P, B*gx*gy*gz), first n_intervals valid.
+ *   point_cell  [P]            : global BEV cell of every frustum point, -1 if dropped
+ *                                (the inverse map the backward pass uses).
+ *   cell_start  [B*G + 1]      : exclusive prefix of points per BEV cell.
+ *   counts      [4]            : {n_kept, n_intervals, 0, 0}; read back by the host to slice.
+ */
+int rcb_voxel_pooling_prepare_v2(const rcb_prepare_desc *d, const float *coor, int *ranks_bev,
+                                 int *ranks_depth, int *ranks_feat, int *interval_starts,
+                                 int *interval_lengths, int *point_cell, int *cell_start,
+                                 int *counts, void *workspace, size_t workspace_bytes, int device,
+                                 rcb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Rows F, B, L -- bev_pool_v2_forward / bev_pool_v2_backward
+ *   (mmdet3d/ops/bev_pool_v2/src/bev_pool.cpp:30-57, 74-104; kernels bev_pool_cuda.cu:21-48, 67-121)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int n_points;    /* K = ranks_*.numel()                                                        */
+  int n_intervals; /* I = interval_lengths.size(0)                 (bev_pool.cpp:40)             */
+  int C;           /* channels = feat.size(4)                      (bev_pool.cpp:39)             */
+  int B, Z, Y, X;  /* bev_feat_shape[0..3]                         (bev_pool.py:27)              */
+  int n_depth;     /* depth.numel()  = B*N*D*H*W                                                  */
+  int n_pixels;    /* feat rows      = B*N*H*W                                                    */
+  int D;           /* depth bins      } describe the frustum; needed only for RCB_PLAN_STRUCTURED */
+  int HW;          /* H*W per camera  }                                                           */
+  int layout;      /* RCB_LAYOUT_* of `out` / `out_grad`                                          */
+  int feat_dtype;  /* RCB_DTYPE_* of `feat` (depth, out and all gradients are float32)            */
+  int flags;       /* RCB_PLAN_* bits known to hold for these ranks                               */
+} rcb_pool_desc;
+
+/* Checks the RCB_PLAN_* properties of caller-supplied ranks on the device (the reference trusts
+ * them blindly) and writes the bit mask to *flags_out (device int).  point_cell[n_depth] is
+ * filled with the BEV cell of every depth element (-1 = not referenced): valid as the backward's
+ * inverse map when RCB_PLAN_STRUCTURED comes back set. */
+size_t rcb_pool_validate_workspace_bytes(const rcb_pool_desc *d);
+int rcb_pool_validate(const rcb_pool_desc *d, const int *ranks_depth, const int *ranks_feat,
+                      const int *ranks_bev, const int *interval_starts, const int *interval_lengths,
+                      int *point_cell, int *flags_out, void *workspace, size_t workspace_bytes,
+                      int device, rcb_stream_t stream);
+
+/* cell_start[B*Z*Y*X + 1]: dense CSR over BEV cells (exclusive prefix of points per cell) from
+ * sorted intervals.  Requires RCB_PLAN_SORTED_CELLS.  rcb_voxel_pooling_prepare_v2 emits the
+ * same array directly. */
+int rcb_pool_build_cellmap(const rcb_pool_desc *d, const int *ranks_bev, const int *interval_starts,
+                           int *cell_start, int device, rcb_stream_t stream);
+
+/*
+ * Forward.  depth: float32 [n_depth]; feat: [n_pixels, C] channels last, `feat_dtype`;
+ * out: float32 [B*Z*Y*X*C] in `layout`, fully written on return (the reference needs it
+ * pre-zeroed, bev_pool.py:27, and a permute copy afterwards, bev_pool.py:91 -- neither here).
+ *   cell_start != NULL (ranks with RCB_PLAN_SORTED_CELLS): tile kernel, one pass.
+ *   cell_start == NULL: general path for arbitrary ranks (memset + one warp per interval).
+ * Argument order of the rank arrays follows bev_pool_v2_forward (bev_pool.cpp:30-38):
+ * interval_lengths BEFORE interval_starts.
+ */
+int rcb_bev_pool_v2_fwd(const rcb_pool_desc *d, const float *depth, const void *feat,
+                        const int *ranks_depth, const int *ranks_feat, const int *ranks_bev,
+                        const int *interval_lengths, const int *interval_starts,
+                        const int *cell_start, float *out, int device, rcb_stream_t stream);
+
+/*
+ * Backward (bev_pool.cpp:74-104).  out_grad float32 in `layout`; depth_grad float32 [n_depth];
+ * feat_grad float32 [n_pixels, C].  Both gradients are fully written (zeros where nothing
+ * contributes; the reference zero-fills them first, bev_pool.py:67-68).
+ *   RCB_PLAN_STRUCTURED + point_cell != NULL: deterministic pixel-stationary kernel; no sort
+ *     (the reference re-sorts by ranks_feat on every call, bev_pool.py:47-57).
+ *   otherwise: general path (depth_grad exact; feat_grad accumulated with float atomics).
+ * workspace >= rcb_pool_bwd_workspace_bytes() (holds out_grad as rows when layout is B_C_CELLS).
+ */
+size_t rcb_pool_bwd_workspace_bytes(const rcb_pool_desc *d);
+int rcb_bev_pool_v2_bwd(const rcb_pool_desc *d, const float *out_grad, const float *depth,
+                        const void *feat, const int *ranks_depth, const int *ranks_feat,
+                        const int *ranks_bev, const int *point_cell, float *depth_grad,
+                        float *feat_grad, void *workspace, size_t workspace_bytes, int device,
+                        rcb_stream_t stream);
+
+/* (n_img, C, HW) with image stride `src_img_stride` elements -> (n_img, HW, C) contiguous.
+ * Replaces the `feat.contiguous()` transpose copy of bev_pool.py:21 and `out_grad.contiguous()`
+ * of bev_pool.py:69.  elem_bytes: 4 (fp32), 2 (bf16/fp16), -2 (fp32 in, bf16 out). */
+int rcb_planes_to_rows(const void *src, void *dst, int n_img, int C, int HW,
+                       long long src_img_stride, int elem_bytes, int device, rcb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row R -- PointPillarsScatterRCS.forward up to the two convolutions
+ *   (mmdet3d/models/middle_encoders/pillar_scatter.py:64-104, 115-131;
+ *    mmdet3d/core/utils/gaussian.py:6-23, 26-55, 57-81)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int V;        /* pillars                                  */
+  int Cin;      /* point feature channels                   */
+  int rcs_dim;  /* columns of rcs (7); RCS value = col rcs_dim-2, x,y = cols 0,1 */
+  int B, ny, nx;
+} rcb_radar_desc;
+
+size_t rcb_radar_workspace_bytes(const rcb_radar_desc *d);
+
+/* point_features (V,Cin) f32; rcs (V,rcs_dim) f32; coors (V,4) int32 [b, z, y, x].
+ * features (B,Cin,ny,nx), heatmap (B,ny,nx), heatmap_feat (B,1,ny,nx): all fully written. */
+int rcb_radar_rcs_scatter(const rcb_radar_desc *d, const float *point_features, const float *rcs,
+                          const int *coors, float *features, float *heatmap, float *heatmap_feat,
+                          void *workspace, size_t workspace_bytes, int device, rcb_stream_t stream);
+
+/* features_grad (B,Cin,ny,nx) -> point_features_grad (V,Cin): the gather that is the scatter's
+ * gradient (only `features` depends on a differentiable input). */
+int rcb_radar_scatter_bwd(const rcb_radar_desc *d, const float *features_grad, const int *coors,
+                          float *point_features_grad, int device, rcb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCBEVDET_B200_H_ */

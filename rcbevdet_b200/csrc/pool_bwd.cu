@@ -1,0 +1,249 @@
+// Row B -- bev_pool_v2 backward.
+// Reference: mmdet3d/ops/bev_pool_v2/bev_pool.py:43-83 (re-sort by ranks_feat, rebuild intervals,
+// zero-filled gradients) and src/bev_pool_cuda.cu:67-121 (one thread per pixel, serial over its
+// points and channels):
+//   depth_grad[ranks_depth[p]]   = sum_c out_grad[ranks_bev[p], c] * feat[ranks_feat[p], c]
+//   feat_grad[ranks_feat[p], c] += out_grad[ranks_bev[p], c] * depth[ranks_depth[p]]
+//
+//  k_pool_bwd_pixels (structured ranks: ranks_depth unique, ranks_feat = pixel of ranks_depth --
+//      what prepare emits): no sort at all.  The points of pixel (b, n, h, w) are the D depth bins
+//      of that pixel, and the inverse map point_cell[P] (BEV cell of each frustum point, -1 =
+//      dropped; a by-product of prepare) says where each went.  One warp per pixel keeps the
+//      pixel's context row in registers, walks its depth column 32 bins at a time, gathers the
+//      out_grad row of each kept bin with one 128-bit load per lane, and produces both gradients:
+//      feat_grad accumulates in registers (written once, zeros for unseen pixels), depth_grad is a
+//      32-way transposed warp reduction (31 shuffles per 32 bins instead of 5 per bin).  Both
+//      outputs are fully written, deterministic, no atomics, no memset.
+//
+//  k_pool_bwd_points (general ranks): one warp per point; depth_grad exact, feat_grad by float
+//      atomics into a zero-filled buffer.
+#include "common.cuh"
+
+namespace rcb {
+
+// sum over lanes of v[k] for every k in [0,32): lane l returns the total of index bitrev-free
+// mapping k = l (see the selects below: at each step the half of the values a lane does not own
+// is sent to its partner).  31 shuffles.
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const bool up = lane & 16;
+    const float send = up ? v[k] : v[k + 16];
+    const float keep = up ? v[k + 16] : v[k];
+    v[k] = keep + __shfl_xor_sync(kFull, send, 16);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const bool up = lane & 8;
+    const float send = up ? v[k] : v[k + 8];
+    const float keep = up ? v[k + 8] : v[k];
+    v[k] = keep + __shfl_xor_sync(kFull, send, 8);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool up = lane & 4;
+    const float send = up ? v[k] : v[k + 4];
+    const float keep = up ? v[k + 4] : v[k];
+    v[k] = keep + __shfl_xor_sync(kFull, send, 4);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const bool up = lane & 2;
+    const float send = up ? v[k] : v[k + 2];
+    const float keep = up ? v[k + 2] : v[k];
+    v[k] = keep + __shfl_xor_sync(kFull, send, 2);
+  }
+  {
+    const bool up = lane & 1;
+    const float send = up ? v[0] : v[1];
+    const float keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(kFull, send, 1);
+  }
+  // lane l now holds the total of index k with bits (16,8,4,2,1) of l selecting the upper half at
+  // each step, i.e. k == l.
+  return v[0];
+}
+
+struct BwdPixelParams {
+  const float *out_grad_rows;  // (n_cells, C) channels last
+  const float *depth;
+  const void *feat;
+  const int *point_cell;
+  float *depth_grad;
+  float *feat_grad;
+  int n_pixels, D, HW, DHW, C4;
+};
+
+// kQ = 128-bit quads per lane (C <= 128*kQ)
+template <typename FeatT, int kQ>
+__global__ void __launch_bounds__(256) k_pool_bwd_pixels(BwdPixelParams p) {
+  const int lane = lane_id();
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const FeatT *feat = static_cast<const FeatT *>(p.feat);
+  const float4 *og_rows = reinterpret_cast<const float4 *>(p.out_grad_rows);
+  for (int pix = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pix < p.n_pixels; pix += warps) {
+    const int bn = pix / p.HW, hw = pix - bn * p.HW;
+    const int col = bn * p.DHW + hw;  // point index of depth bin 0
+    float4 f[kQ], fg[kQ];
+#pragma unroll
+    for (int j = 0; j < kQ; ++j) {
+      const int q = lane + 32 * j;
+      f[j] = q < p.C4 ? Row4<FeatT>::load(feat, (size_t)pix * p.C4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      fg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int d0 = 0; d0 < p.D; d0 += 32) {
+      const int my_d = d0 + lane;
+      int my_cell = -1;
+      float my_w = 0.f;
+      if (my_d < p.D) {
+        my_cell = __ldg(p.point_cell + col + my_d * p.HW);
+        my_w = __ldg(p.depth + col + my_d * p.HW);
+      }
+      float dot[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int cell = __shfl_sync(kFull, my_cell, k);
+        const float w = __shfl_sync(kFull, my_w, k);
+        float s = 0.f;
+        if (cell >= 0) {
+#pragma unroll
+          for (int j = 0; j < kQ; ++j) {
+            const int q = lane + 32 * j;
+            if (q < p.C4) {
+              const float4 g = __ldg(og_rows + (size_t)cell * p.C4 + q);
+              s = fmaf(g.x, f[j].x, s), s = fmaf(g.y, f[j].y, s);
+              s = fmaf(g.z, f[j].z, s), s = fmaf(g.w, f[j].w, s);
+              fg[j].x = fmaf(g.x, w, fg[j].x), fg[j].y = fmaf(g.y, w, fg[j].y);
+              fg[j].z = fmaf(g.z, w, fg[j].z), fg[j].w = fmaf(g.w, w, fg[j].w);
+            }
+          }
+        }
+        dot[k] = s;
+      }
+      const float total = transpose_reduce32(dot, lane);
+      if (my_d < p.D) p.depth_grad[col + my_d * p.HW] = total;
+    }
+#pragma unroll
+    for (int j = 0; j < kQ; ++j) {
+      const int q = lane + 32 * j;
+      if (q < p.C4) reinterpret_cast<float4 *>(p.feat_grad)[(size_t)pix * p.C4 + q] = fg[j];
+    }
+  }
+}
+
+// General ranks: warp per point.
+template <typename FeatT>
+__global__ void __launch_bounds__(256)
+    k_pool_bwd_points(int n_points, int C, const float *__restrict__ out_grad_rows,
+                      const float *__restrict__ depth, const FeatT *__restrict__ feat,
+                      const int *__restrict__ ranks_depth, const int *__restrict__ ranks_feat,
+                      const int *__restrict__ ranks_bev, float *__restrict__ depth_grad,
+                      float *__restrict__ feat_grad) {
+  const int lane = lane_id();
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_points; i += warps) {
+    const int rd = __ldg(ranks_depth + i), rf = __ldg(ranks_feat + i), rb = __ldg(ranks_bev + i);
+    const float w = __ldg(depth + rd);
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float g = __ldg(out_grad_rows + (size_t)rb * C + c);
+      s = fmaf(g, to_f32<FeatT>(feat[(size_t)rf * C + c]), s);
+      atomicAdd(feat_grad + (size_t)rf * C + c, g * w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+    if (lane == 0) depth_grad[rd] = s;
+  }
+}
+
+int planes_to_rows_launch(const void *src, void *dst, int n_img, int C, int HW,
+                          long long src_img_stride, int elem_bytes, cudaStream_t s);
+
+template <typename FeatT>
+static int launch_pixels(BwdPixelParams &p, int sms, cudaStream_t s) {
+  const int grid = max(1, min(ceil_div(p.n_pixels, 8), sms * 32));
+  if (p.C4 <= 32)
+    k_pool_bwd_pixels<FeatT, 1><<<grid, 256, 0, s>>>(p);
+  else
+    k_pool_bwd_pixels<FeatT, 2><<<grid, 256, 0, s>>>(p);
+  RCB_LAUNCH_CHECK();
+  return RCB_OK;
+}
+
+}  // namespace rcb
+
+using namespace rcb;
+
+extern "C" size_t rcb_pool_bwd_workspace_bytes(const rcb_pool_desc *d) {
+  if (check_pool_desc(d) != RCB_OK) return 0;
+  if (d->layout != RCB_LAYOUT_B_C_CELLS) return 256;
+  return align_up((size_t)d->B * d->Z * d->Y * d->X * d->C * 4, 256);
+}
+
+extern "C" int rcb_bev_pool_v2_bwd(const rcb_pool_desc *d, const float *out_grad, const float *depth,
+                                   const void *feat, const int *ranks_depth, const int *ranks_feat,
+                                   const int *ranks_bev, const int *point_cell, float *depth_grad,
+                                   float *feat_grad, void *workspace, size_t workspace_bytes,
+                                   int device, rcb_stream_t stream) {
+  int rc = check_pool_desc(d);
+  if (rc != RCB_OK) return rc;
+  if (!out_grad || !depth || !feat || !depth_grad || !feat_grad) return RCB_ERR_ARG;
+  DeviceGuard guard(device);
+  if (guard.err) return guard.err;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int cps = d->Z * d->Y * d->X;
+  const int sms = sm_count_cached(device);
+
+  // out_grad as channels-last rows (the reference gets them from permute-backward + .contiguous(),
+  // bev_pool.py:69,91)
+  const float *og_rows = out_grad;
+  if (d->layout == RCB_LAYOUT_B_C_CELLS) {
+    const size_t need = (size_t)d->B * cps * d->C * 4;
+    if (!workspace || workspace_bytes < need) return RCB_ERR_WORKSPACE;
+    rc = planes_to_rows_launch(out_grad, workspace, d->B, d->C, cps, (long long)d->C * cps, 4, s);
+    if (rc != RCB_OK) return rc;
+    og_rows = static_cast<const float *>(workspace);
+  }
+
+  const int elem = d->feat_dtype == RCB_DTYPE_F32 ? 4 : 2;
+  const bool structured = (d->flags & RCB_PLAN_STRUCTURED) && point_cell != nullptr && d->D > 0 &&
+                          d->HW > 0 && (d->C % 4) == 0 && d->C <= 256 &&
+                          (((uintptr_t)feat) % (4 * elem)) == 0 && (((uintptr_t)og_rows) % 16) == 0 &&
+                          (((uintptr_t)feat_grad) % 16) == 0 &&
+                          (long long)d->n_pixels * d->D == (long long)d->n_depth;
+  if (structured) {
+    BwdPixelParams p;
+    p.out_grad_rows = og_rows, p.depth = depth, p.feat = feat, p.point_cell = point_cell;
+    p.depth_grad = depth_grad, p.feat_grad = feat_grad;
+    p.n_pixels = d->n_pixels, p.D = d->D, p.HW = d->HW, p.DHW = d->D * d->HW, p.C4 = d->C / 4;
+    switch (d->feat_dtype) {
+      case RCB_DTYPE_F32: return launch_pixels<float>(p, sms, s);
+      case RCB_DTYPE_BF16: return launch_pixels<__nv_bfloat16>(p, sms, s);
+      default: return launch_pixels<__half>(p, sms, s);
+    }
+  }
+  // general path (bev_pool.py:67-68 zero-fill, then accumulate)
+  RCB_CUDA_TRY(cudaMemsetAsync(depth_grad, 0, (size_t)d->n_depth * 4, s));
+  RCB_CUDA_TRY(cudaMemsetAsync(feat_grad, 0, (size_t)d->n_pixels * d->C * 4, s));
+  if (d->n_points == 0) return RCB_OK;
+  if (!ranks_depth || !ranks_feat || !ranks_bev) return RCB_ERR_ARG;
+  const int grid = max(1, min(ceil_div(d->n_points, 8), sms * 32));
+  switch (d->feat_dtype) {
+    case RCB_DTYPE_F32:
+      k_pool_bwd_points<float><<<grid, 256, 0, s>>>(d->n_points, d->C, og_rows, depth,
+                                                    static_cast<const float *>(feat), ranks_depth,
+                                                    ranks_feat, ranks_bev, depth_grad, feat_grad);
+      break;
+    case RCB_DTYPE_BF16:
+      k_pool_bwd_points<__nv_bfloat16><<<grid, 256, 0, s>>>(
+          d->n_points, d->C, og_rows, depth, static_cast<const __nv_bfloat16 *>(feat), ranks_depth,
+          ranks_feat, ranks_bev, depth_grad, feat_grad);
+      break;
+    default:
+      k_pool_bwd_points<__half><<<grid, 256, 0, s>>>(d->n_points, d->C, og_rows, depth,
+                                                     static_cast<const __half *>(feat), ranks_depth,
+                                                     ranks_feat, ranks_bev, depth_grad, feat_grad);
+  }
+  RCB_LAUNCH_CHECK();
+  return RCB_OK;
+}

@@ -190,3 +190,47 @@ def radar_pillars(batch, ny, nx, points_per_sample=3125, in_channels=64, seed=4,
         rcss.append(r)
         coors.append(c)
     return (torch.cat(feats).to(device), torch.cat(rcss).to(device), torch.cat(coors).to(device))
+
+
+def frustum(depth_cfg, input_size, downsample, device="cpu"):
+    """(D, H, W, 3) float32 image-plane frustum (u, v, d): pixel centres on a linspace over the
+    input image, depth bins arange(*depth_cfg) -- the template of view_transformer.py:85-113."""
+    H_in, W_in = input_size
+    Hf, Wf = H_in // downsample, W_in // downsample
+    d = torch.arange(*depth_cfg, dtype=torch.float32, device=device)
+    u = torch.linspace(0, W_in - 1, Wf, dtype=torch.float32, device=device)
+    v = torch.linspace(0, H_in - 1, Hf, dtype=torch.float32, device=device)
+    D = d.shape[0]
+    return torch.stack((u.view(1, 1, Wf).expand(D, Hf, Wf), v.view(1, Hf, 1).expand(D, Hf, Wf),
+                        d.view(D, 1, 1).expand(D, Hf, Wf)), -1)
+
+
+def _apply3(m, p):
+    """(..., 3, 3) applied to (..., D, H, W, 3) with explicit fp32 multiply-adds (no BLAS, so the
+    result does not depend on the host's GEMM kernels)."""
+    m = m[..., None, None, None, :, :]
+    return (m[..., :, 0] * p[..., 0:1] + m[..., :, 1] * p[..., 1:2]) + m[..., :, 2] * p[..., 2:3]
+
+
+def lidar_coor(calib, depth_cfg, input_size, downsample):
+    """Frustum points in the ego/lidar frame, (B, N, D, H, W, 3) float32: undo the image
+    augmentation, un-project with the intrinsics, move to the ego frame, apply the BEV
+    augmentation (the geometry of view_transformer.py:115-157).  Input synthesis for tests and
+    benchmarks; parity of the pooling path is defined on `coor`, whatever produced it."""
+    s2e, _e2g, intrin, post_rot, post_tran, bda = calib
+    dev = s2e.device
+    fr = frustum(depth_cfg, input_size, downsample, device=dev)
+    pts = fr[None, None] - post_tran[:, :, None, None, None, :]
+    pts = _apply3(torch.linalg.inv(post_rot.double()).float(), pts)
+    pts = torch.cat((pts[..., :2] * pts[..., 2:3], pts[..., 2:3]), -1)
+    combine = (s2e[:, :, :3, :3].double() @ torch.linalg.inv(intrin.double())).float()
+    pts = _apply3(combine, pts) + s2e[:, :, None, None, None, :3, 3]
+    return _apply3(bda[:, None], pts).contiguous()
+
+
+def grid_tensors(grid):
+    """(grid_lower_bound, grid_interval, grid_size) as the fp32 tensors the reference builds in
+    create_grid_infos (view_transformer.py:80-83)."""
+    cfgs = [grid["x"], grid["y"], grid["z"]]
+    return (torch.Tensor([c[0] for c in cfgs]), torch.Tensor([c[2] for c in cfgs]),
+            torch.Tensor([(c[1] - c[0]) / c[2] for c in cfgs]))

@@ -1,0 +1,65 @@
+"""LSSViewTransformer.voxel_pooling_v2 (mmdet3d/models/necks/view_transformer.py:180-205) as one
+device-side chain: prepare -> pool, with no host synchronisation in between.
+
+The reference method must read four sizes back to the host (boolean-mask compactions, `where`)
+before it can launch the pool kernel.  The tile kernel here is driven by the dense per-cell CSR
+that prepare leaves on the device, so neither the number of kept points nor the number of
+intervals is needed on the host; an empty result (no point inside the grid) simply comes out as
+zeros, which is what the reference's special case returns (:184-194).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib, bev_pool as _bp, plan as _plan
+from .prepare import prepare_async
+
+
+class _ViewPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, feat, prepared):
+        dev = depth.device
+        depth_c = depth.detach().contiguous().float()
+        rows = _bp.feat_rows(feat.detach())
+        gz, gy, gx = prepared.grid
+        C = rows.shape[1]
+        d = _lib.PoolDesc()
+        d.n_points, d.n_intervals, d.C = prepared.P, 0, C   # upper bounds; the tile kernel reads the CSR
+        d.B, d.Z, d.Y, d.X = prepared.B, gz, gy, gx
+        d.n_depth, d.n_pixels = depth_c.numel(), rows.shape[0]
+        d.D, d.HW = prepared.D, prepared.HW
+        d.layout, d.feat_dtype, d.flags = _lib.LAYOUT_B_C_CELLS, _bp._DTYPES[rows.dtype], _lib.PLAN_ALL
+        if d.n_depth != prepared.P or d.n_pixels * d.D != d.n_depth:
+            raise ValueError("depth / feat shapes do not match the frustum that `coor` describes")
+        out = torch.empty((prepared.B, C, gz, gy, gx), dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().rcb_bev_pool_v2_fwd(
+            ctypes.byref(d), _lib.ptr(depth_c), _lib.ptr(rows), _lib.ptr(prepared.ranks_depth),
+            _lib.ptr(prepared.ranks_feat), _lib.ptr(prepared.ranks_bev), None, None,
+            _lib.ptr(prepared.cell_start), _lib.ptr(out), dev.index, _lib.stream_ptr(dev)),
+            "rcb_bev_pool_v2_fwd")
+        ctx.save_for_backward(depth_c, rows, prepared.ranks_depth, prepared.ranks_feat, prepared.ranks_bev)
+        plan = _plan.PoolPlan(_lib.PLAN_ALL, prepared.cell_start, prepared.point_cell, prepared.D,
+                              prepared.HW, prepared.n_cells, prepared.P)
+        ctx.rcb = (d, plan, tuple(feat.shape), feat.dtype, tuple(depth.shape), depth.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        desc, plan, feat_shape, feat_dtype, depth_shape, depth_dtype = ctx.rcb
+        depth_grad, feat_grad = _bp._backward(out_grad, ctx.saved_tensors, desc, plan, feat_shape,
+                                              feat_dtype, depth_shape, depth_dtype)
+        return depth_grad, feat_grad, None
+
+
+def voxel_pooling_v2(coor, depth, feat, grid_lower_bound, grid_interval, grid_size, collapse_z=True,
+                     return_prepared=False):
+    """coor (B,N,D,H,W,3) fp32; depth (B,N,D,H,W); feat (B,N,C,H,W) -- exactly the arguments of
+    the reference method.  Returns bev_feat (B, C*Z, Y, X) (collapse_z) or (B,C,Z,Y,X)."""
+    prepared = prepare_async(coor, grid_lower_bound, grid_interval, grid_size)
+    feat = feat.permute(0, 1, 3, 4, 2)                       # view_transformer.py:195
+    bev = _ViewPool.apply(depth, feat, prepared)
+    if collapse_z:
+        bev = torch.cat(bev.unbind(dim=2), 1)                # view_transformer.py:203-204
+    return (bev, prepared) if return_prepared else bev
