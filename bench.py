@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""Benchmark of the camera->BEV pooling hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the hot path over one batch of the R50 workload (BASELINE config 2:
+B=8 samples x 6 cameras x D118 x 16x44, C=80 -> 128x128 BEV) per GPU:
+    voxel_pooling_prepare_v2  ->  context transpose  ->  bev_pool_v2 forward  ->  backward
+exactly what a training step of the reference runs with accelerate=False
+(mmdet3d/models/necks/view_transformer.py:180-205, mmdet3d/ops/bev_pool_v2/bev_pool.py).
+Weak scaling: every rank pools its own 8 samples, no collective on the data path.
+
+Rank 0 prints ONE JSON line.  `value` = samples/s with inputs resident in HBM (CUDA events, max
+over ranks); `e2e` = the same step through the public API from pinned HOST buffers, host<->device
+copies inside the timed region; `roofline` = the dominant kernel against the measured HBM peak;
+`cpu_baseline` = the CPU oracle (C, OpenMP) timed on this box's host cores (N=1, rank 0).
+`--impl reference` times that CPU implementation alone (the reference has no CPU pool kernel;
+/root/reference is absent on the GPU box, so the restatement in oracle/ is what runs).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "bev_pool_samples_per_s"
+UNIT = "samples/s"
+WORKLOAD = dict(workload="RCBEVDet R50 256x704 LSS view transform: prepare + bev_pool_v2 fwd+bwd, "
+                         "B=8/GPU, 6 cams, D=118, 16x44 features, C=80 -> 128x128 BEV (BASELINE config 2)",
+                batch_per_gpu=8, cams=6, D=118, H=16, W=44, C=80, bev=[1, 128, 128])
+N_SETS = 3  # rotating input sets
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------------
+# clocks: NVML sampled from a thread during the timed region
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, torch_device_index):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(torch_device_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            self.nv = pynvml
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def _sample(self):
+        try:
+            self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            bits = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            for b, name in self.REASONS.items():
+                if bits & b and name != "gpu_idle":
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self._sample()
+            time.sleep(0.002)
+
+    def start(self):
+        if self.ok:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join()
+        if self.ok and not self.samples:
+            self._sample()
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------
+# workload
+# --------------------------------------------------------------------------------------------
+def make_inputs(torch, rig, device, B, seed):
+    """One input set on `device` (host tensors when device == 'cpu'): the key frame of B samples,
+    per-sample ego jitter so the sets differ.  coor comes from the frustum geometry."""
+    motion = rig.temporal_motion(B, 2, seed=seed).view(B, 2, 3)[:, 1]
+    calib = rig.camera_rig(B, input_size=rig.R50_INPUT, frame_motion=motion)
+    coor = rig.lidar_coor(calib, rig.R50_GRID["depth"], rig.R50_INPUT, 16)
+    _, N, D, H, W, _ = coor.shape
+    depth, feat = rig.pooling_inputs(B, N, D, H, W, WORKLOAD["C"], seed=seed)
+    out_grad = torch.randn(B, WORKLOAD["C"], 1, 128, 128, generator=torch.Generator().manual_seed(seed + 2))
+    return tuple(t.to(device) for t in (coor, depth, feat, out_grad))
+
+
+def algorithmic_bytes(K, I, B):
+    """bytes each stage must move at minimum (4-byte words)."""
+    w = WORKLOAD
+    P = B * w["cams"] * w["D"] * w["H"] * w["W"]
+    F = B * w["cams"] * w["H"] * w["W"]
+    G = B * 128 * 128
+    C = w["C"]
+    return {"prepare": 12 * P + 12 * K + 8 * I,
+            "fwd": 4 * (K + F * C + 2 * K + 3 * I + G * C),
+            "bwd": 4 * (I * C + K + F * C + 3 * K + P + F * C)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import rcbevdet_b200 as rcb
+    from rcbevdet_b200 import _lib, bev_pool as bp, rig
+    from rcbevdet_b200.prepare import prepare_async
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: rcbevdet_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    lib = _lib.lib()
+    B, C = WORKLOAD["batch_per_gpu"], WORKLOAD["C"]
+    lo, iv, sz = rig.grid_tensors(rig.R50_GRID)
+    sets = [make_inputs(torch, rig, dev, B, seed=100 * rank + 10 * s + 1) for s in range(N_SETS)]
+    stream = torch.cuda.current_stream(dev)
+
+    stage_names = ("prepare", "feat_rows", "fwd", "bwd")
+    n_kernels = {"prepare": 5, "feat_rows": 1, "fwd": 1, "bwd": 2}
+    stage_events = {s: [] for s in stage_names}
+
+    def step(i, record):
+        coor, depth, feat, out_grad = sets[i % N_SETS]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if record else None
+        if record:
+            ev[0].record(stream)
+        prepared = prepare_async(coor, lo, iv, sz)                               # row P
+        if record:
+            ev[1].record(stream)
+        rows = bp.feat_rows(feat.permute(0, 1, 3, 4, 2))                         # bev_pool.py:21
+        if record:
+            ev[2].record(stream)
+        d = _lib.PoolDesc()
+        d.n_points, d.n_intervals, d.C = prepared.P, 0, C
+        d.B, d.Z, d.Y, d.X = B, 1, 128, 128
+        d.n_depth, d.n_pixels, d.D, d.HW = depth.numel(), rows.shape[0], prepared.D, prepared.HW
+        d.layout, d.feat_dtype, d.flags = _lib.LAYOUT_B_C_CELLS, _lib.DTYPE_F32, _lib.PLAN_ALL
+        out = torch.empty((B, C, 1, 128, 128), dtype=torch.float32, device=dev)
+        _lib.check(lib.rcb_bev_pool_v2_fwd(ctypes.byref(d), _lib.ptr(depth), _lib.ptr(rows),
+                                           _lib.ptr(prepared.ranks_depth), _lib.ptr(prepared.ranks_feat),
+                                           _lib.ptr(prepared.ranks_bev), None, None, _lib.ptr(prepared.cell_start),
+                                           _lib.ptr(out), dev.index, _lib.stream_ptr(dev)), "fwd")   # row F
+        if record:
+            ev[3].record(stream)
+        depth_grad = torch.empty_like(depth)
+        feat_grad = torch.empty_like(rows)
+        ws_bytes = lib.rcb_pool_bwd_workspace_bytes(ctypes.byref(d))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.rcb_bev_pool_v2_bwd(ctypes.byref(d), _lib.ptr(out_grad), _lib.ptr(depth), _lib.ptr(rows),
+                                           _lib.ptr(prepared.ranks_depth), _lib.ptr(prepared.ranks_feat),
+                                           _lib.ptr(prepared.ranks_bev), _lib.ptr(prepared.point_cell),
+                                           _lib.ptr(depth_grad), _lib.ptr(feat_grad), _lib.ptr(ws), ws_bytes,
+                                           dev.index, _lib.stream_ptr(dev)), "bwd")                # row B
+        if record:
+            ev[4].record(stream)
+            for k, s in enumerate(stage_names):
+                stage_events[s].append((ev[k], ev[k + 1]))
+        return prepared, out, depth_grad, feat_grad
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up, then EXACTLY K timed steps ------------------------------------------------
+    for i in range(args.warmup):
+        last = step(i, False)
+    torch.cuda.synchronize(dev)
+    prepared = last[0]
+    K_pts, I_iv = (int(v) for v in prepared.counts[:2].tolist())
+    checksum = float(last[1].double().sum().item())
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for i in range(args.steps):
+        step(i, True)
+    t1.record(stream)
+    barrier()
+    clk = clocks.stop()
+    total_ms = t0.elapsed_time(t1)
+    stage_ms = {s: sum(a.elapsed_time(b) for a, b in stage_events[s]) / args.steps for s in stage_names}
+
+    # ---- end to end through the public API from pinned host buffers --------------------------
+    host_sets = [tuple(t.pin_memory() for t in make_inputs(torch, rig, "cpu", B, seed=100 * rank + 10 * s + 1))
+                 for s in range(2)]
+    host_out = [torch.empty((B, C, 128, 128), dtype=torch.float32).pin_memory(),
+                torch.empty(host_sets[0][1].shape, dtype=torch.float32).pin_memory(),
+                torch.empty(host_sets[0][2].shape, dtype=torch.float32).pin_memory()]
+    h2d = sum(t.numel() * t.element_size() for t in host_sets[0])
+    d2h = sum(t.numel() * t.element_size() for t in host_out)
+
+    def e2e_step(i):
+        hc, hd, hf, hg = host_sets[i % 2]
+        coor = hc.to(dev, non_blocking=True)
+        depth = hd.to(dev, non_blocking=True).requires_grad_(True)
+        feat = hf.to(dev, non_blocking=True).requires_grad_(True)
+        og = hg.to(dev, non_blocking=True)
+        bev = rcb.voxel_pooling_v2(coor, depth, feat, lo, iv, sz)                # public API (row V)
+        bev.backward(og.view(bev.shape))
+        host_out[0].copy_(bev.detach(), non_blocking=True)
+        host_out[1].copy_(depth.grad, non_blocking=True)
+        host_out[2].copy_(feat.grad, non_blocking=True)
+        torch.cuda.synchronize(dev)                                              # results are on the host
+
+    e2e_steps = max(3, min(args.steps, 50))
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    w0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    barrier()
+    e2e_s = time.perf_counter() - w0
+
+    # ---- max over ranks ----------------------------------------------------------------------
+    times = torch.tensor([total_ms, e2e_s * 1e3] + [stage_ms[s] for s in stage_names], dtype=torch.float64,
+                         device=dev)
+    sums = torch.tensor([checksum], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        gathered = [torch.zeros_like(sums) for _ in range(world)]
+        dist.all_gather(gathered, sums)            # NCCL only for verification/reporting
+        checks = [float(g.item()) for g in gathered]
+    else:
+        checks = [checksum]
+    total_ms, e2e_ms = float(times[0]), float(times[1])
+    stage_ms = {s: float(times[2 + k]) for k, s in enumerate(stage_names)}
+    ms_per_step = total_ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+    e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        alg = algorithmic_bytes(K_pts, I_iv, B)
+        kernel_stage = max(("prepare", "fwd", "bwd"), key=lambda s: stage_ms[s])
+        kernel_names = {"prepare": "prepare pipeline (k_point_cells..k_sort_cells_*)", "fwd": "k_pool_fwd_tile",
+                        "bwd": "k_planes_to_rows + k_pool_bwd_pixels"}
+        achieved = alg[kernel_stage] / (stage_ms[kernel_stage] * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(kernel_stage)
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(WORKLOAD, parallelism=f"sample-sharded x{world}, no data-path collective",
+                           l2=f"rotating {N_SETS} input sets (~117 MB each) + ~250 MB of outputs/workspace per "
+                              "step: every step's working set exceeds the 126 MB L2",
+                           kept_points=K_pts, intervals=I_iv),
+            "clocks": clk,
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "rcbevdet_b200.voxel_pooling_v2 + autograd backward, pinned host buffers"},
+            "gpu_launches": args.steps * sum(n_kernels.values()),
+            "stages_ms": {s: round(v, 5) for s, v in stage_ms.items()},
+            "stage_frac_of_hbm_peak": {s: round(alg[s] / (stage_ms[s] * 1e-3) / 1e9 / peak, 4)
+                                       for s in ("prepare", "fwd", "bwd")},
+            "prepare_plus_fwd": {"samples_per_s": round(world * B / ((stage_ms["prepare"] + stage_ms["feat_rows"] +
+                                                                      stage_ms["fwd"]) * 1e-3), 1),
+                                 "frac_of_hbm_peak": round((alg["prepare"] + alg["fwd"]) /
+                                                           ((stage_ms["prepare"] + stage_ms["feat_rows"] +
+                                                             stage_ms["fwd"]) * 1e-3) / 1e9 / peak, 4)},
+            "roofline": {"bound": "hbm", "kernel": kernel_names[kernel_stage], "achieved": round(achieved, 1),
+                         "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[kernel_stage]},
+            "checksums": checks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_budget)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle's compiled restatement of the reference path, all host threads
+# --------------------------------------------------------------------------------------------
+def _cpu_step_fn(samples, threads):
+    import numpy as np
+    import torch
+
+    from oracle import oracle
+    from rcbevdet_b200 import rig
+
+    coor, depth, feat, og = make_inputs(torch, rig, "cpu", samples, seed=1)
+    lo, iv, sz = (t.numpy() for t in rig.grid_tensors(rig.R50_GRID))
+    coor, depth = coor.numpy(), depth.numpy()
+    feat_v = feat.permute(0, 1, 3, 4, 2)
+    og_v = og.view(samples, WORKLOAD["C"], 1, 128, 128).permute(0, 2, 3, 4, 1)
+    shape = (samples, 1, 128, 128, WORKLOAD["C"])
+
+    def step():
+        rb, rd, rf, st, ln = oracle.voxel_pooling_prepare_v2_c(coor, lo, iv, sz, threads=threads)
+        rows = np.ascontiguousarray(feat_v.numpy())                              # bev_pool.py:21
+        out = oracle.bev_pool_v2_forward(depth, rows, rd, rf, rb, shape, st, ln, threads=threads)
+        bev = oracle.to_bczyx(out)                                               # bev_pool.py:91
+        g_rows = np.ascontiguousarray(og_v.numpy())                              # bev_pool.py:69
+        dg, fg = oracle.bev_pool_v2_backward(g_rows, depth, rows, rd, rf, rb, threads=threads)
+        return bev, dg, fg
+
+    return step
+
+
+def cpu_baseline(budget_s=15.0):
+    threads = os.cpu_count() or 1
+    step = _cpu_step_fn(1, threads)
+    step()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        step()
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 200:
+            break
+    return {"value": round(n / dt, 2), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} single-sample steps (prepare + fwd + bwd, same geometry) in {dt:.1f} s; "
+                      "oracle/bevpool_oracle.c with OpenMP"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    # bound the run: samples per step chosen so K + W steps end within ~2 minutes
+    probe = _cpu_step_fn(1, threads)
+    probe()
+    t0 = time.perf_counter()
+    probe()
+    t1 = time.perf_counter() - t0
+    budget = 120.0
+    per_step = max(1, min(WORKLOAD["batch_per_gpu"], int(budget / max(args.steps + args.warmup, 1) / max(t1, 1e-6))))
+    step = _cpu_step_fn(per_step, threads) if per_step != 1 else probe
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = (f"{per_step} sample(s) per step x {args.steps} steps; prepare + fwd + bwd of the same geometry; "
+              "CPU restatement of the reference path (oracle/bevpool_oracle.c, OpenMP)")
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": dict(WORKLOAD, parallelism="host CPU threads", samples_per_step=per_step),
+            "cpu_baseline": {"value": round(value, 2), "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": round(value, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=30)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -102,6 +102,30 @@ def voxel_pooling_prepare_v2(coor, lower, interval, size):
             interval_starts, interval_lengths)
 
 
+def voxel_pooling_prepare_v2_c(coor, lower, interval, size, threads=1):
+    """Same contract as voxel_pooling_prepare_v2 above, computed by the compiled C restatement
+    (bevpool_oracle.c, stable counting sort).  Used as the timed CPU baseline."""
+    coor = np.ascontiguousarray(coor, dtype=np.float32)
+    B, N, D, H, W, _ = coor.shape
+    P = B * N * D * H * W
+    n_cells = int(B * int(size[0]) * int(size[1]) * int(size[2]))
+    fp, ip = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)
+    lo, iv, sz = (np.ascontiguousarray(a, dtype=np.float32) for a in (lower, interval, size))
+    rb, rd, rf = (np.empty(max(P, 1), np.int32) for _ in range(3))
+    st, ln = (np.empty(max(1, min(P, n_cells)), np.int32) for _ in range(2))
+    counts = np.zeros(4, np.int32)
+    rc = _lib().oracle_voxel_pooling_prepare_v2(
+        B, N, D, H, W, coor.ctypes.data_as(fp), lo.ctypes.data_as(fp), iv.ctypes.data_as(fp),
+        sz.ctypes.data_as(fp), rb.ctypes.data_as(ip), rd.ctypes.data_as(ip), rf.ctypes.data_as(ip),
+        st.ctypes.data_as(ip), ln.ctypes.data_as(ip), counts.ctypes.data_as(ip), int(threads))
+    if rc != 0:
+        raise RuntimeError("oracle_voxel_pooling_prepare_v2 failed")
+    k, i = int(counts[0]), int(counts[1])
+    if k == 0:
+        return None, None, None, None, None
+    return rb[:k], rd[:k], rf[:k], st[:i], ln[:i]
+
+
 def canonicalise(ranks_bev, ranks_depth, ranks_feat):
     """Lexicographic (ranks_bev, ranks_depth) order.  Lossless because every
     ranks_depth value is unique; removes the reference's unspecified tie order."""
@@ -140,6 +164,8 @@ def _lib():
         _clib.oracle_bev_pool_v2_bwd.argtypes = [ctypes.c_int, ctypes.c_int, fp, fp, fp, ip, ip, ip, ip, ip,
                                                  fp, fp, ctypes.c_int]
         _clib.oracle_bev_pool_v2_bwd.restype = None
+        _clib.oracle_voxel_pooling_prepare_v2.argtypes = [ctypes.c_int] * 5 + [fp] * 4 + [ip] * 6 + [ctypes.c_int]
+        _clib.oracle_voxel_pooling_prepare_v2.restype = ctypes.c_int
     return _clib
 
 

@@ -75,9 +75,19 @@ struct Row4<float> {
   static __device__ __forceinline__ float4 load(const float *base, size_t quad) {
     return __ldg(reinterpret_cast<const float4 *>(base) + quad);
   }
+  static __device__ __forceinline__ float4 load_bytes(const char *p) {
+    return __ldg(reinterpret_cast<const float4 *>(p));
+  }
 };
 template <>
 struct Row4<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 load_bytes(const char *p) {
+    uint2 raw = __ldg(reinterpret_cast<const uint2 *>(p));
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162 *>(&raw.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162 *>(&raw.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+  }
   static __device__ __forceinline__ float4 load(const __nv_bfloat16 *base, size_t quad) {
     uint2 raw = __ldg(reinterpret_cast<const uint2 *>(base) + quad);
     __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162 *>(&raw.x);
@@ -88,6 +98,13 @@ struct Row4<__nv_bfloat16> {
 };
 template <>
 struct Row4<__half> {
+  static __device__ __forceinline__ float4 load_bytes(const char *p) {
+    uint2 raw = __ldg(reinterpret_cast<const uint2 *>(p));
+    __half2 a = *reinterpret_cast<__half2 *>(&raw.x);
+    __half2 b = *reinterpret_cast<__half2 *>(&raw.y);
+    float2 fa = __half22float2(a), fb = __half22float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+  }
   static __device__ __forceinline__ float4 load(const __half *base, size_t quad) {
     uint2 raw = __ldg(reinterpret_cast<const uint2 *>(base) + quad);
     __half2 a = *reinterpret_cast<__half2 *>(&raw.x);
@@ -105,6 +122,26 @@ template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 template <>
 __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+
+// Exact unsigned 32-bit division by a run-time constant (Granlund-Montgomery round-up method):
+// q = (t + ((n - t) >> s1)) >> s2 with t = umulhi(m, n).  Valid for every n < 2^32, d >= 1.
+struct FastDiv {
+  unsigned m, s1, s2, d;
+  __host__ static FastDiv make(unsigned d) {
+    FastDiv f;
+    unsigned l = 0;
+    while ((1ull << l) < d) ++l;
+    f.m = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    f.s1 = l < 1 ? l : 1;
+    f.s2 = l > 0 ? l - 1 : 0;
+    f.d = d;
+    return f;
+  }
+  __device__ __forceinline__ unsigned div(unsigned n) const {
+    const unsigned t = __umulhi(m, n);
+    return (t + ((n - t) >> s1)) >> s2;
+  }
+};
 
 struct DeviceGuard {
   int prev = -1;

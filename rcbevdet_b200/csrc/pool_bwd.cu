@@ -131,6 +131,125 @@ __global__ void __launch_bounds__(256) k_pool_bwd_pixels(BwdPixelParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Half-warp variant (C a multiple of 16): 16 lanes per pixel, two adjacent pixels per warp, each
+// lane owning kNQ 128-bit quads (channels 64*j + 4*l .. +3) and kNS scalars (channels
+// 64*kNQ + 16*s + l).  C = 80 -> one quad + one scalar per lane: no idle lanes (the 32-lane
+// kernel above runs 20 of 32), half the shuffles per point, and the 16-way transposed
+// reduction costs 15 shuffles per 16 depth bins.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float transpose_reduce16(float (&v)[16], int l16) {
+#pragma unroll
+  for (int h = 8; h >= 1; h >>= 1) {
+#pragma unroll
+    for (int k = 0; k < h; ++k) {
+      const bool up = l16 & h;
+      const float send = up ? v[k] : v[k + h];
+      const float keep = up ? v[k + h] : v[k];
+      v[k] = keep + __shfl_xor_sync(kFull, send, h);
+    }
+  }
+  return v[0];  // lane l16 holds the total of index l16
+}
+
+template <typename T>
+struct Elem;
+template <>
+struct Elem<float> {
+  static __device__ __forceinline__ float load(const char *p) { return __ldg(reinterpret_cast<const float *>(p)); }
+};
+template <>
+struct Elem<__nv_bfloat16> {
+  static __device__ __forceinline__ float load(const char *p) {
+    return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16 *>(p)));
+  }
+};
+template <>
+struct Elem<__half> {
+  static __device__ __forceinline__ float load(const char *p) {
+    return __half2float(__ldg(reinterpret_cast<const __half *>(p)));
+  }
+};
+
+template <typename FeatT, int kNQ, int kNS>
+__global__ void __launch_bounds__(256, 3) k_pool_bwd_pixels16(BwdPixelParams p) {
+  constexpr int kC = 64 * kNQ + 16 * kNS;
+  const int lane = lane_id(), l16 = lane & 15, half = lane >> 4;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const char *og = reinterpret_cast<const char *>(p.out_grad_rows);
+  const char *feat = static_cast<const char *>(p.feat);
+  for (int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pair * 2 < p.n_pixels; pair += warps) {
+    const int pix = pair * 2 + half;
+    const bool live = pix < p.n_pixels;
+    const int pix_c = live ? pix : p.n_pixels - 1;
+    const int bn = pix_c / p.HW, hw = pix_c - bn * p.HW;
+    const int col = bn * p.DHW + hw;  // point index of depth bin 0
+    float4 fq[kNQ > 0 ? kNQ : 1], gq[kNQ > 0 ? kNQ : 1];
+    float fs[kNS > 0 ? kNS : 1], gs[kNS > 0 ? kNS : 1];
+    const char *frow = feat + (size_t)pix_c * kC * sizeof(FeatT);
+#pragma unroll
+    for (int j = 0; j < kNQ; ++j) {
+      fq[j] = Row4<FeatT>::load_bytes(frow + (64 * j + 4 * l16) * sizeof(FeatT));
+      gq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < kNS; ++j) {
+      fs[j] = Elem<FeatT>::load(frow + (64 * kNQ + 16 * j + l16) * sizeof(FeatT));
+      gs[j] = 0.f;
+    }
+    const char *og_lane = og + (size_t)l16 * 16;
+    for (int d0 = 0; d0 < p.D; d0 += 16) {
+      const int my_d = d0 + l16;
+      int my_cell = -1;
+      float my_w = 0.f;
+      if (live && my_d < p.D) {
+        my_cell = __ldg(p.point_cell + col + my_d * p.HW);
+        my_w = __ldg(p.depth + col + my_d * p.HW);
+      }
+      float dot[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int cell = __shfl_sync(kFull, my_cell, k, 16);
+        const float w = __shfl_sync(kFull, my_w, k, 16);
+        float s = 0.f;
+        if (cell >= 0) {
+          const char *row = og_lane + (size_t)cell * (kC * 4);
+          const float2 ww = make_float2(w, w);
+          float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < kNQ; ++j) {
+            const float4 g = __ldg(reinterpret_cast<const float4 *>(row + 256 * j));
+            const float2 glo = make_float2(g.x, g.y), ghi = make_float2(g.z, g.w);
+            acc = __ffma2_rn(glo, make_float2(fq[j].x, fq[j].y), acc);
+            acc = __ffma2_rn(ghi, make_float2(fq[j].z, fq[j].w), acc);
+            const float2 a = __ffma2_rn(glo, ww, make_float2(gq[j].x, gq[j].y));
+            const float2 b = __ffma2_rn(ghi, ww, make_float2(gq[j].z, gq[j].w));
+            gq[j] = make_float4(a.x, a.y, b.x, b.y);
+          }
+          s = acc.x + acc.y;
+#pragma unroll
+          for (int j = 0; j < kNS; ++j) {
+            // scalar tail: channel 64*kNQ + 16*j + l16
+            const float g = __ldg(reinterpret_cast<const float *>(row + (256 * kNQ + 64 * j) - 12 * l16));
+            s = fmaf(g, fs[j], s);
+            gs[j] = fmaf(g, w, gs[j]);
+          }
+        }
+        dot[k] = s;
+      }
+      const float total = transpose_reduce16(dot, l16);
+      if (live && my_d < p.D) p.depth_grad[col + my_d * p.HW] = total;
+    }
+    if (live) {
+      float *grow = p.feat_grad + (size_t)pix * kC;
+#pragma unroll
+      for (int j = 0; j < kNQ; ++j) *reinterpret_cast<float4 *>(grow + 64 * j + 4 * l16) = gq[j];
+#pragma unroll
+      for (int j = 0; j < kNS; ++j) grow[64 * kNQ + 16 * j + l16] = gs[j];
+    }
+  }
+}
+
 // General ranks: warp per point.
 template <typename FeatT>
 __global__ void __launch_bounds__(256)
@@ -161,6 +280,15 @@ int planes_to_rows_launch(const void *src, void *dst, int n_img, int C, int HW,
 
 template <typename FeatT>
 static int launch_pixels(BwdPixelParams &p, int sms, cudaStream_t s) {
+  const int C = p.C4 * 4;
+  const int grid16 = max(1, min(ceil_div(p.n_pixels, 16), sms * 24));
+  if (C == 80 || C == 64 || C == 128) {
+    if (C == 80) k_pool_bwd_pixels16<FeatT, 1, 1><<<grid16, 256, 0, s>>>(p);
+    else if (C == 64) k_pool_bwd_pixels16<FeatT, 1, 0><<<grid16, 256, 0, s>>>(p);
+    else k_pool_bwd_pixels16<FeatT, 2, 0><<<grid16, 256, 0, s>>>(p);
+    RCB_LAUNCH_CHECK();
+    return RCB_OK;
+  }
   const int grid = max(1, min(ceil_div(p.n_pixels, 8), sms * 32));
   if (p.C4 <= 32)
     k_pool_bwd_pixels<FeatT, 1><<<grid, 256, 0, s>>>(p);

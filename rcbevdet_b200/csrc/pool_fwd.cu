@@ -27,11 +27,13 @@
 namespace rcb {
 
 constexpr int kTileX = 8;
-constexpr int kTileY = 8;
-constexpr int kTileCells = kTileX * kTileY;
-constexpr int kStageCap = 2048;  // points staged per round
+constexpr int kTileY = 4;
+constexpr int kTileCells = kTileX * kTileY;   // 32: one warp describes the patch, lane <-> cell
+constexpr int kGroups = 16;                   // lane-groups (of C/4 threads) per CTA
+constexpr int kStagePerThread = 4;            // points staged per thread and round
 constexpr int kMinItem = 32;
-constexpr int kFwdMinCtas = 2;
+constexpr int kMaxItems = kTileCells + kGroups;
+constexpr int kFwdTableBytes = 1024;
 
 struct FwdTileParams {
   const float *depth;
@@ -41,53 +43,77 @@ struct FwdTileParams {
   const int *cell_start;
   float *out;
   int C, C4;
-  int n_groups;          // lane-groups per CTA = blockDim.x / C4
   int X, R;              // cells per row, rows per sample (Z*Y)
   int tiles_x, tiles_r;  // patches per sample
   int cells_per_sample;
   int layout;
 };
 
-struct StagePoint {
+struct __align__(8) StagePoint {
   float w;
-  int row;
+  unsigned row_bytes;  // ranks_feat * C * sizeof(FeatT): byte offset of the context row
 };
 
-__host__ __device__ inline size_t fwd_tile_smem_bytes(int C, int n_groups) {
-  const int max_items = n_groups + kTileCells;
-  size_t b = 0;
-  b += (size_t)kStageCap * sizeof(StagePoint);
-  b += (size_t)max_items * C * 4;          // part
-  b += (size_t)kTileCells * (C + 1) * 4;   // res
-  b += (size_t)max_items * 3 * 4;          // item_cell/lo/hi
-  b += (size_t)kTileCells * 4 * 4;         // cell_lo, cell_hi, cell_item0, cell_items
-  b += 64 * 4;                             // seg tables + scalars
-  return b;
+__host__ __device__ inline int fwd_part_pitch(int C) { return C + 4; }  // floats; +4 keeps 16-byte rows and
+                                                                        // spreads cells over banks
+__host__ __device__ inline size_t fwd_tile_smem_bytes(int C) {
+  const size_t stage = (size_t)kStagePerThread * kGroups * (C / 4) * sizeof(StagePoint);
+  const size_t part = (size_t)kMaxItems * fwd_part_pitch(C) * 4;
+  return ((stage + part + 15) / 16) * 16 + kFwdTableBytes;
 }
 
-// kC4 > 0: channels/4 known at compile time (index arithmetic by constants); 0: runtime.
+__device__ __forceinline__ void fma_row(float4 &acc, const float4 v, const float w) {
+  const float2 ww = make_float2(w, w);
+  float2 lo = __ffma2_rn(make_float2(v.x, v.y), ww, make_float2(acc.x, acc.y));
+  float2 hi = __ffma2_rn(make_float2(v.z, v.w), ww, make_float2(acc.z, acc.w));
+  acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+// sum_i w_i * row_i over staged points [i, hi): fused multiply-adds in point order (the
+// reference's order), kUnroll independent 128-bit row loads in flight
+template <typename FeatT, int kUnroll>
+__device__ __forceinline__ float4 accumulate_range(const StagePoint *__restrict__ stage,
+                                                   const char *__restrict__ feat_q, int i, int hi) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (; i + kUnroll <= hi; i += kUnroll) {
+    StagePoint sp[kUnroll];
+    float4 v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) sp[u] = stage[i + u];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) v[u] = Row4<FeatT>::load_bytes(feat_q + sp[u].row_bytes);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) fma_row(acc, v[u], sp[u].w);
+  }
+  for (; i < hi; ++i) {
+    const StagePoint s0 = stage[i];
+    fma_row(acc, Row4<FeatT>::load_bytes(feat_q + s0.row_bytes), s0.w);
+  }
+  return acc;
+}
+
+// kC4 > 0: channels/4 known at compile time; 0: run time (C4 even).  blockDim.x == kGroups * C4,
+// i.e. C4 / 2 warps, and every warp combines / writes two 128-bit channel quads of all 32 cells.
 template <typename FeatT, int kC4>
-__global__ void __launch_bounds__(kC4 ? kC4 * 32 : 1024, (kC4 && kC4 * 32 <= 640) ? kFwdMinCtas : 1)
+__global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ? 3 : 2) : 1)
     k_pool_fwd_tile(FwdTileParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C4 = kC4 ? kC4 : p.C4;
-  const int C = C4 * 4, NG = p.n_groups;
-  const int max_items = NG + kTileCells;
+  const int C = C4 * 4;
+  const int pitch = fwd_part_pitch(C);
+  const int stage_cap = kStagePerThread * blockDim.x;
   StagePoint *stage = reinterpret_cast<StagePoint *>(smem_raw);
-  float *part = reinterpret_cast<float *>(stage + kStageCap);
-  float *res = part + (size_t)max_items * C;
-  int *item_cell = reinterpret_cast<int *>(res + kTileCells * (C + 1));
-  int *item_lo = item_cell + max_items;
-  int *item_hi = item_lo + max_items;
-  int *cell_lo = item_hi + max_items;
-  int *cell_hi = cell_lo + kTileCells;
-  int *cell_item0 = cell_hi + kTileCells;
-  int *cell_items = cell_item0 + kTileCells;
-  int *seg_off = cell_items + kTileCells;   // [kTileY + 1] patch-local prefix of row slices
-  int *seg_g = seg_off + kTileY + 1;        // [kTileY] global start of each row slice
-  int *s_nitems = seg_g + kTileY;
+  float *part = reinterpret_cast<float *>(stage + stage_cap);
+  int *tab = reinterpret_cast<int *>(smem_raw + fwd_tile_smem_bytes(C) - kFwdTableBytes);
+  int *cell_lo = tab;          // [32] patch-local point range of every cell
+  int *cell_hi = tab + 32;     // [32]
+  int *seg_off = tab + 64;     // [kTileY + 1] patch-local prefix of the row slices
+  int *seg_g = tab + 72;       // [kTileY] global start of each row slice
+  int *cell_item0 = tab + 80;  // [33] first item of each cell in this round
+  int *item_lo = tab + 116;    // [kMaxItems] staged range of each item
+  int *item_hi = tab + 116 + kMaxItems;
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
   int t = blockIdx.x;
   const int tx_i = t % p.tiles_x;
   t /= p.tiles_x;
@@ -97,8 +123,8 @@ __global__ void __launch_bounds__(kC4 ? kC4 * 32 : 1024, (kC4 && kC4 * 32 <= 640
   const int nx = min(kTileX, p.X - x0), nr = min(kTileY, p.R - r0);
   const int cell_base = b * p.cells_per_sample;
 
-  // ---- patch geometry: one thread per cell reads its CSR range -----------------------------
-  if (tid < kTileCells) {
+  // ---- patch geometry, by warp 0: lane <-> cell ----------------------------------------------
+  if (tid < 32) {
     const int ty = tid / kTileX, tx = tid % kTileX;
     int s = 0, e = 0;
     if (ty < nr && tx < nx) {
@@ -106,64 +132,65 @@ __global__ void __launch_bounds__(kC4 ? kC4 * 32 : 1024, (kC4 && kC4 * 32 <= 640
       s = __ldg(p.cell_start + c);
       e = __ldg(p.cell_start + c + 1);
     }
-    cell_lo[tid] = s;  // global for now
-    cell_hi[tid] = e;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int off = 0;
-    for (int ty = 0; ty < kTileY; ++ty) {
-      seg_off[ty] = off;
-      int g = 0, n = 0;
-      if (ty < nr) {
-        g = cell_lo[ty * kTileX];
-        n = cell_hi[ty * kTileX + nx - 1] - g;
-      }
-      seg_g[ty] = g;
-      off += n;
+    // row slice = [start of its first cell, end of its last valid cell)
+    int off = 0, my_off = 0, my_g = 0;
+#pragma unroll
+    for (int r = 0; r < kTileY; ++r) {
+      const int g = __shfl_sync(kFull, s, r * kTileX);
+      const int ge = __shfl_sync(kFull, e, r * kTileX + nx - 1);
+      const int len = r < nr ? ge - g : 0;
+      if (r == ty) my_off = off, my_g = g;
+      if (tid == r) seg_off[r] = off, seg_g[r] = g;
+      off += len;
     }
-    seg_off[kTileY] = off;
+    if (tid == 0) seg_off[kTileY] = off;
+    cell_lo[tid] = s - my_g + my_off;
+    cell_hi[tid] = e - my_g + my_off;
   }
   __syncthreads();
   const int total = seg_off[kTileY];
-  if (tid < kTileCells) {  // global -> patch-local coordinates
-    const int ty = tid / kTileX;
-    const int shift = seg_off[ty] - seg_g[ty];
-    cell_lo[tid] += shift;
-    cell_hi[tid] += shift;
-  }
-  for (int i = tid; i < kTileCells * (C + 1); i += blockDim.x) res[i] = 0.f;
-  __syncthreads();
 
   const int group = tid / C4, q = tid - group * C4;
-  const FeatT *feat = static_cast<const FeatT *>(p.feat);
+  const char *feat_q = static_cast<const char *>(p.feat) + (size_t)q * 4 * sizeof(FeatT);
+  const unsigned row_stride = (unsigned)C * sizeof(FeatT);
+  // combine / write role: lane <-> cell, this warp's quads are warp and warp + n_warps
+  float4 racc[2];
+  racc[0] = racc[1] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (int cb = 0; cb < total; cb += kStageCap) {
-    const int n = min(kStageCap, total - cb);
-    // ---- stage (weight, row) of the round's points; build the item list ----------------------
-    for (int i = tid; i < n; i += blockDim.x) {
-      const int pt = cb + i;
-      int ty = 0;
+  for (int cb = 0; cb < total; cb += stage_cap) {
+    const int n = min(stage_cap, total - cb);
+    // ---- stage (depth weight, context row offset): all index loads first, then the gathers ----
+    {
+      int g[kStagePerThread], rd[kStagePerThread];
+      unsigned rf[kStagePerThread];
 #pragma unroll
-      for (int k = 1; k < kTileY; ++k) ty += (pt >= seg_off[k]);
-      const int g = seg_g[ty] + (pt - seg_off[ty]);
-      const int rd = ld_stream_s32(p.ranks_depth + g);
-      StagePoint sp;
-      sp.row = ld_stream_s32(p.ranks_feat + g);
-      sp.w = __ldg(p.depth + rd);
-      stage[i] = sp;
-    }
-    const int L = max(kMinItem, ceil_div(n, NG));
-    if (tid < 32) {  // warp 0: items per cell (2 cells per lane), exclusive scan, emit
-      int a[2], bnd[2], cnt[2];
+      for (int k = 0; k < kStagePerThread; ++k) {
+        const int pt = cb + tid + k * blockDim.x;
+        int ty = 0;
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int j = tid * 2 + k;
-        a[k] = max(cell_lo[j], cb);
-        bnd[k] = min(cell_hi[j], cb + n);
-        cnt[k] = bnd[k] > a[k] ? ceil_div(bnd[k] - a[k], L) : 0;
+        for (int r = 1; r < kTileY; ++r) ty += (pt >= seg_off[r]);
+        g[k] = tid + k * blockDim.x < n ? seg_g[ty] + (pt - seg_off[ty]) : -1;
       }
-      const int mine = cnt[0] + cnt[1];
+#pragma unroll
+      for (int k = 0; k < kStagePerThread; ++k) {
+        rd[k] = g[k] >= 0 ? ld_stream_s32(p.ranks_depth + g[k]) : 0;
+        rf[k] = g[k] >= 0 ? (unsigned)ld_stream_s32(p.ranks_feat + g[k]) : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < kStagePerThread; ++k) {
+        if (g[k] >= 0) {
+          StagePoint sp;
+          sp.row_bytes = rf[k] * row_stride;
+          sp.w = ld_stream_f32(p.depth + rd[k]);  // used once per cell: keep it out of L1
+          stage[tid + k * blockDim.x] = sp;
+        }
+      }
+    }
+    // ---- work items: every cell is cut into pieces of <= L points, L >= n / kGroups ----------
+    const int L = max(kMinItem, ceil_div(n, kGroups));
+    if (tid < 32) {
+      const int a = max(cell_lo[tid], cb), bnd = min(cell_hi[tid], cb + n);
+      const int mine = bnd > a ? ceil_div(bnd - a, L) : 0;
       int incl = mine;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -171,87 +198,54 @@ __global__ void __launch_bounds__(kC4 ? kC4 * 32 : 1024, (kC4 && kC4 * 32 <= 640
         if (tid >= o) incl += v;
       }
       int off = incl - mine;
-      if (tid == 31) *s_nitems = incl;
+      cell_item0[tid] = off;
+      if (tid == 31) cell_item0[32] = incl;
+      for (int k = 0; k < mine; ++k, ++off) {
+        item_lo[off] = a + k * L - cb;
+        item_hi[off] = min(bnd, a + (k + 1) * L) - cb;
+      }
+    }
+    __syncthreads();
+    // ---- items round-robin over the lane-groups ---------------------------------------------
+    const int n_items = cell_item0[32];
+    for (int it = group; it < n_items; it += kGroups) {
+      const float4 acc = accumulate_range<FeatT, 8>(stage, feat_q, item_lo[it], item_hi[it]);
+      *reinterpret_cast<float4 *>(part + (size_t)it * pitch + q * 4) = acc;
+    }
+    __syncthreads();
+    // ---- fixed-order combine into the writer's registers -------------------------------------
+    {
+      const int i0 = cell_item0[lane], i1 = cell_item0[lane + 1];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        const int j = tid * 2 + k;
-        cell_item0[j] = off;
-        cell_items[j] = cnt[k];
-        for (int s = 0; s < cnt[k]; ++s) {
-          item_cell[off] = j;
-          item_lo[off] = a[k] + s * L - cb;
-          item_hi[off] = min(bnd[k], a[k] + (s + 1) * L) - cb;
-          ++off;
+        const int qq = warp + k * n_warps;
+        for (int it = i0; it < i1; ++it) {
+          const float4 v = *reinterpret_cast<const float4 *>(part + (size_t)it * pitch + qq * 4);
+          racc[k].x += v.x, racc[k].y += v.y, racc[k].z += v.z, racc[k].w += v.w;
         }
       }
     }
-    __syncthreads();
-    // ---- items: sequential fused multiply-adds in point order (the reference's order) --------
-    const int n_items = *s_nitems;
-    if (group < NG) {
-      for (int it = group; it < n_items; it += NG) {
-        int i = item_lo[it];
-        const int hi = item_hi[it];
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (; i + 4 <= hi; i += 4) {
-          const StagePoint s0 = stage[i], s1 = stage[i + 1], s2 = stage[i + 2], s3 = stage[i + 3];
-          const float4 v0 = Row4<FeatT>::load(feat, (size_t)s0.row * C4 + q);
-          const float4 v1 = Row4<FeatT>::load(feat, (size_t)s1.row * C4 + q);
-          const float4 v2 = Row4<FeatT>::load(feat, (size_t)s2.row * C4 + q);
-          const float4 v3 = Row4<FeatT>::load(feat, (size_t)s3.row * C4 + q);
-          acc.x = fmaf(v0.x, s0.w, acc.x), acc.y = fmaf(v0.y, s0.w, acc.y);
-          acc.z = fmaf(v0.z, s0.w, acc.z), acc.w = fmaf(v0.w, s0.w, acc.w);
-          acc.x = fmaf(v1.x, s1.w, acc.x), acc.y = fmaf(v1.y, s1.w, acc.y);
-          acc.z = fmaf(v1.z, s1.w, acc.z), acc.w = fmaf(v1.w, s1.w, acc.w);
-          acc.x = fmaf(v2.x, s2.w, acc.x), acc.y = fmaf(v2.y, s2.w, acc.y);
-          acc.z = fmaf(v2.z, s2.w, acc.z), acc.w = fmaf(v2.w, s2.w, acc.w);
-          acc.x = fmaf(v3.x, s3.w, acc.x), acc.y = fmaf(v3.y, s3.w, acc.y);
-          acc.z = fmaf(v3.z, s3.w, acc.z), acc.w = fmaf(v3.w, s3.w, acc.w);
-        }
-        for (; i < hi; ++i) {
-          const StagePoint s0 = stage[i];
-          const float4 v0 = Row4<FeatT>::load(feat, (size_t)s0.row * C4 + q);
-          acc.x = fmaf(v0.x, s0.w, acc.x), acc.y = fmaf(v0.y, s0.w, acc.y);
-          acc.z = fmaf(v0.z, s0.w, acc.z), acc.w = fmaf(v0.w, s0.w, acc.w);
-        }
-        *reinterpret_cast<float4 *>(part + (size_t)it * C + q * 4) = acc;
-      }
-    }
-    __syncthreads();
-    // ---- fixed-order combine of each cell's items ---------------------------------------------
-    for (int idx = tid; idx < kTileCells * C4; idx += blockDim.x) {
-      const int j = idx / C4, qq = idx - j * C4;
-      const int k0 = cell_item0[j], kn = cell_items[j];
-      if (kn > 0) {
-        float4 s = *reinterpret_cast<const float4 *>(part + (size_t)k0 * C + qq * 4);
-        for (int k = 1; k < kn; ++k) {
-          const float4 v = *reinterpret_cast<const float4 *>(part + (size_t)(k0 + k) * C + qq * 4);
-          s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
-        }
-        float *r = res + j * (C + 1) + qq * 4;
-        r[0] += s.x, r[1] += s.y, r[2] += s.z, r[3] += s.w;
-      }
-    }
-    __syncthreads();
+    if (cb + stage_cap < total) __syncthreads();  // stage / part / tables are rewritten next round
   }
 
-  // ---- write the whole patch, empty cells included ------------------------------------------
-  if (p.layout == RCB_LAYOUT_B_C_CELLS) {
-    const int per_c = nr * nx;
-    float *out_b = p.out + (size_t)b * C * p.cells_per_sample + (size_t)r0 * p.X + x0;
-    for (int idx = tid; idx < C * per_c; idx += blockDim.x) {
-      const int c = idx / per_c, rem = idx - c * per_c;
-      const int ty = rem / nx, tx = rem - ty * nx;
-      st_stream_f32(out_b + (size_t)c * p.cells_per_sample + ty * p.X + tx,
-                    res[(ty * kTileX + tx) * (C + 1) + c]);
-    }
+  // ---- write the whole patch, empty cells included: lane <-> cell ---------------------------
+  const int ty = lane / kTileX, tx = lane % kTileX;
+  if (ty >= nr || tx >= nx) return;
+  const size_t cell_in_sample = (size_t)(r0 + ty) * p.X + x0 + tx;
+  if (p.layout == RCB_LAYOUT_CELLS_C) {
+    float4 *dst = reinterpret_cast<float4 *>(p.out + ((size_t)cell_base + cell_in_sample) * C);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) st_stream_f4(dst + warp + k * n_warps, racc[k]);
   } else {
-    const int per_row = nx * C;
-    for (int idx = tid; idx < nr * per_row; idx += blockDim.x) {
-      const int ty = idx / per_row, rem = idx - ty * per_row;
-      const int tx = rem / C, c = rem - tx * C;
-      st_stream_f32(p.out + ((size_t)cell_base + (size_t)(r0 + ty) * p.X + x0 + tx) * C + c,
-                    res[(ty * kTileX + tx) * (C + 1) + c]);
+    // (B, C, cells): every store instruction writes kTileY runs of kTileX consecutive cells
+    float *dst = p.out + (size_t)b * C * p.cells_per_sample + cell_in_sample;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      float *d4 = dst + (size_t)(warp + k * n_warps) * 4 * p.cells_per_sample;
+      st_stream_f32(d4, racc[k].x);
+      st_stream_f32(d4 + p.cells_per_sample, racc[k].y);
+      st_stream_f32(d4 + 2 * (size_t)p.cells_per_sample, racc[k].z);
+      st_stream_f32(d4 + 3 * (size_t)p.cells_per_sample, racc[k].w);
     }
   }
 }
@@ -302,8 +296,8 @@ __global__ void __launch_bounds__(256)
 
 template <typename FeatT, int kC4>
 static int launch_tile_c4(const rcb_pool_desc *d, FwdTileParams &p, cudaStream_t s) {
-  const int threads = p.n_groups * p.C4;
-  const size_t smem = fwd_tile_smem_bytes(p.C, p.n_groups);
+  const int threads = kGroups * p.C4;
+  const size_t smem = fwd_tile_smem_bytes(p.C);
   RCB_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd_tile<FeatT, kC4>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long grid = (long long)d->B * p.tiles_r * p.tiles_x;
@@ -365,7 +359,7 @@ extern "C" int rcb_bev_pool_v2_fwd(const rcb_pool_desc *d, const float *depth, c
   const size_t out_bytes = (size_t)d->B * cps * d->C * 4;
 
   const int elem = d->feat_dtype == RCB_DTYPE_F32 ? 4 : 2;
-  const bool tile_ok = cell_start != nullptr && (d->C % 4) == 0 && d->C <= 256 &&
+  const bool tile_ok = cell_start != nullptr && (d->C % 8) == 0 && d->C <= 256 && (long long)d->n_pixels * d->C * elem < (1ll << 32) &&
                        (((uintptr_t)feat) % (4 * elem)) == 0;
   if (tile_ok) {
     if (d->n_points > 0 && (!depth || !feat || !ranks_depth || !ranks_feat)) return RCB_ERR_ARG;
@@ -373,7 +367,6 @@ extern "C" int rcb_bev_pool_v2_fwd(const rcb_pool_desc *d, const float *depth, c
     p.depth = depth, p.feat = feat, p.ranks_depth = ranks_depth, p.ranks_feat = ranks_feat;
     p.cell_start = cell_start, p.out = out;
     p.C = d->C, p.C4 = d->C / 4;
-    p.n_groups = max(1, min(32, 1024 / p.C4));
     p.X = d->X, p.R = d->Z * d->Y;
     p.tiles_x = ceil_div(p.X, kTileX), p.tiles_r = ceil_div(p.R, kTileY);
     p.cells_per_sample = cps, p.layout = d->layout;
@@ -402,3 +395,9 @@ extern "C" int rcb_bev_pool_v2_fwd(const rcb_pool_desc *d, const float *depth, c
                                       interval_starts, interval_lengths, out, sms, s);
   }
 }
+
+#ifdef RCB_PROFILE_PHASES
+extern "C" int rcb_debug_fwd_prof(long long *host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, rcb::g_fwd_prof, sizeof(long long) * n);
+}
+#endif

@@ -78,10 +78,11 @@ def test_ragged_shapes(shape):
     _check_against_oracle(coor, lo, iv, sz)
 
 
-@pytest.mark.parametrize("n_cells_hit,P", [(1, 40), (1, 64), (1, 65), (3, 3000), (2, 9000), (5, 20001)])
+@pytest.mark.parametrize("n_cells_hit,P", [(1, 32), (1, 33), (1, 40), (1, 64), (1, 65), (1, 100), (1, 128), (1, 129), (1, 200), (1, 256), (1, 257), (1, 500), (1, 512), (1, 513), (1, 1024), (1, 1025),
+                                          (2, 300), (7, 900), (3, 3000), (2, 9000), (5, 20001)])
 def test_long_cells_every_sort_tier(n_cells_hit, P):
-    """Cells with 33..4096 points (shared-memory bitonic) and > 4096 points (in-place global
-    bitonic), incl. non-power-of-two lengths."""
+    """Cells with <= 256 points (register bitonic, 1/2/4/8 values per lane), 257..4096 points
+    (shared-memory bitonic) and > 4096 points (in-place global bitonic), incl. non-power-of-two lengths."""
     rng = np.random.default_rng(P)
     coor = np.empty((1, 1, P, 1, 1, 3), np.float32)
     which = rng.integers(0, n_cells_hit, size=P)

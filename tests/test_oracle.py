@@ -52,6 +52,17 @@ def test_prepare_matches_reference_golden(golden_prepare, name):
     assert np.array_equal(crd, rd) and np.array_equal(crf, rf) and np.array_equal(crb, rb)
 
 
+@pytest.mark.parametrize("name", PREP_CASES + ["emptyC"])
+@pytest.mark.parametrize("threads", [1, 4])
+def test_c_prepare_equals_numpy_prepare(golden_prepare, name, threads):
+    """The compiled restatement used as the timed CPU baseline is the same function."""
+    g = golden_prepare
+    args = (g[f"{name}.coor"], g[f"{name}.lower"], g[f"{name}.interval"], g[f"{name}.size"])
+    a, b = oracle.voxel_pooling_prepare_v2(*args), oracle.voxel_pooling_prepare_v2_c(*args, threads=threads)
+    for x, y in zip(a, b):
+        assert (x is None and y is None) or np.array_equal(x, y)
+
+
 def test_prepare_empty(golden_prepare):
     g = golden_prepare
     assert int(g["emptyC.empty"]) == 1
