@@ -47,12 +47,23 @@ struct FwdTileParams {
   int tiles_x, tiles_r;  // patches per sample
   int cells_per_sample;
   int layout;
+  int B;
 };
 
 struct __align__(8) StagePoint {
   float w;
   unsigned row_bytes;  // ranks_feat * C * sizeof(FeatT): byte offset of the context row
 };
+
+// i-th element of {c, c-1, c+1, c-2, c+2, ...} clipped to [0, n), c = n / 2
+__device__ __forceinline__ int zigzag_from_centre(int i, int n) {
+  const int c = n >> 1;
+  const int lo_side = c, hi_side = n - 1 - c;           // elements below / above the centre
+  const int paired = 2 * min(lo_side, hi_side) + 1;     // prefix that alternates
+  if (i < paired) return (i & 1) ? c - ((i + 1) >> 1) : c + (i >> 1);
+  const int rest = i - paired;                          // one side is exhausted
+  return lo_side > hi_side ? c - hi_side - 1 - rest : c + lo_side + 1 + rest;
+}
 
 __host__ __device__ inline int fwd_part_pitch(int C) { return C + 4; }  // floats; +4 keeps 16-byte rows and
                                                                         // spreads cells over banks
@@ -68,6 +79,13 @@ __device__ __forceinline__ void fma_row(float4 &acc, const float4 v, const float
   float2 hi = __ffma2_rn(make_float2(v.z, v.w), ww, make_float2(acc.z, acc.w));
   acc = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
+
+#ifdef RCB_PROFILE_PHASES
+__device__ long long g_fwd_prof[8192 * 8];
+#define RCB_T(k) if (threadIdx.x == 0 && blockIdx.x < 8192) g_fwd_prof[blockIdx.x * 8 + (k)] = clock64();
+#else
+#define RCB_T(k)
+#endif
 
 // sum_i w_i * row_i over staged points [i, hi): fused multiply-adds in point order (the
 // reference's order), kUnroll independent 128-bit row loads in flight
@@ -113,12 +131,16 @@ __global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ?
   int *item_lo = tab + 116;    // [kMaxItems] staged range of each item
   int *item_hi = tab + 116 + kMaxItems;
 
+  RCB_T(0)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
+  // Launch order: patches nearest the grid centre first, samples interleaved.  Point density
+  // peaks around the ego vehicle (a patch there holds ~8x the average), so the long patches start
+  // at once instead of forming the kernel's tail.  Any order is correct; this one is a heuristic.
   int t = blockIdx.x;
-  const int tx_i = t % p.tiles_x;
-  t /= p.tiles_x;
-  const int tr_i = t % p.tiles_r;
-  const int b = t / p.tiles_r;
+  const int b = t % p.B;
+  t /= p.B;
+  const int tx_i = zigzag_from_centre(t % p.tiles_x, p.tiles_x);
+  const int tr_i = zigzag_from_centre(t / p.tiles_x, p.tiles_r);
   const int x0 = tx_i * kTileX, r0 = tr_i * kTileY;
   const int nx = min(kTileX, p.X - x0), nr = min(kTileY, p.R - r0);
   const int cell_base = b * p.cells_per_sample;
@@ -148,7 +170,11 @@ __global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ?
     cell_hi[tid] = e - my_g + my_off;
   }
   __syncthreads();
+  RCB_T(1)
   const int total = seg_off[kTileY];
+#ifdef RCB_PROFILE_PHASES
+  if (threadIdx.x == 0 && blockIdx.x < 8192) g_fwd_prof[blockIdx.x * 8 + 7] = total;
+#endif
 
   const int group = tid / C4, q = tid - group * C4;
   const char *feat_q = static_cast<const char *>(p.feat) + (size_t)q * 4 * sizeof(FeatT);
@@ -206,6 +232,7 @@ __global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ?
       }
     }
     __syncthreads();
+    if (cb == 0) { RCB_T(2) }
     // ---- items round-robin over the lane-groups ---------------------------------------------
     const int n_items = cell_item0[32];
     for (int it = group; it < n_items; it += kGroups) {
@@ -213,6 +240,7 @@ __global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ?
       *reinterpret_cast<float4 *>(part + (size_t)it * pitch + q * 4) = acc;
     }
     __syncthreads();
+    if (cb == 0) { RCB_T(3) }
     // ---- fixed-order combine into the writer's registers -------------------------------------
     {
       const int i0 = cell_item0[lane], i1 = cell_item0[lane + 1];
@@ -228,6 +256,7 @@ __global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ?
     if (cb + stage_cap < total) __syncthreads();  // stage / part / tables are rewritten next round
   }
 
+  RCB_T(4)
   // ---- write the whole patch, empty cells included: lane <-> cell ---------------------------
   const int ty = lane / kTileX, tx = lane % kTileX;
   if (ty >= nr || tx >= nx) return;
@@ -369,7 +398,7 @@ extern "C" int rcb_bev_pool_v2_fwd(const rcb_pool_desc *d, const float *depth, c
     p.C = d->C, p.C4 = d->C / 4;
     p.X = d->X, p.R = d->Z * d->Y;
     p.tiles_x = ceil_div(p.X, kTileX), p.tiles_r = ceil_div(p.R, kTileY);
-    p.cells_per_sample = cps, p.layout = d->layout;
+    p.cells_per_sample = cps, p.layout = d->layout, p.B = d->B;
     switch (d->feat_dtype) {
       case RCB_DTYPE_F32: return launch_tile<float>(d, p, s);
       case RCB_DTYPE_BF16: return launch_tile<__nv_bfloat16>(d, p, s);

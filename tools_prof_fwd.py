@@ -15,17 +15,14 @@ buf=(ctypes.c_longlong*(8192*8))()
 lib.rcb_debug_fwd_prof.argtypes=[ctypes.c_void_p, ctypes.c_int]
 print('rc', lib.rcb_debug_fwd_prof(buf, 8192*8))
 a=np.array(buf[:4096*8]).reshape(4096,8)
-t0=a[:,0].min()
 tot=a[:,7]
-d=np.diff(a[:,:7],axis=1)
-names=['geom','stage+tab','own items','extras+combine','(round0 end)->loop end','res write+sync']
-print('CTA lifetime mean', (a[:,6]-a[:,0]).mean(), 'max', (a[:,6]-a[:,0]).max(), ' kernel span', (a[:,6].max()-t0))
-for k,n in enumerate(names): print(f'{n:28s} mean {d[:,k].mean():9.0f}  p50 {np.median(d[:,k]):9.0f} max {d[:,k].max():9.0f}')
-sel=(tot>500)&(tot<900)
-print('typical tiles (500-900 pts):', sel.sum())
-for k,n in enumerate(names): print(f'   {n:28s} mean {d[sel,k].mean():9.0f}')
-# start time distribution
-st=np.sort(a[:,0]-t0)
-print('start times: p10 %d p50 %d p90 %d max %d' % (st[409], st[2048], st[3686], st[-1]))
-heavy=np.argsort(-tot)[:8]
-for h in heavy: print('heavy tile', h, 'pts', tot[h], 'start', a[h,0]-t0, 'life', a[h,6]-a[h,0])
+ne=tot>0
+life=(a[:,4]-a[:,0])
+print('nonempty tiles', ne.sum(), 'life mean', life[ne].mean(), 'max', life[ne].max(), 'empty life', life[~ne].mean() if (~ne).any() else 0)
+names=['geom','stage+table (round0)','items (round0)','combine+later rounds']
+d=np.diff(a[:,:5],axis=1)
+for lo,hi in [(1,300),(300,900),(900,1500),(1500,3000),(3000,10000)]:
+    sel=(tot>=lo)&(tot<hi)
+    if sel.sum()==0: continue
+    print(f'tiles with {lo}-{hi} pts: {sel.sum()}  life {life[sel].mean():.0f}  ' + '  '.join(f'{n} {d[sel,k].mean():.0f}' for k,n in enumerate(names)))
+print('sum of lifetimes / (148*3 slots) =', life.sum()/(148*3), 'cycles')
