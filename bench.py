@@ -176,7 +176,7 @@ def run_ours(args):
         d = _lib.PoolDesc()
         d.n_points, d.n_intervals, d.C = prepared.P, 0, C
         d.B, d.Z, d.Y, d.X = B, 1, 128, 128
-        d.n_depth, d.n_pixels, d.D, d.HW = depth.numel(), rows.shape[0], prepared.D, prepared.HW
+        d.n_depth, d.n_pixels, d.D, d.HW, d.H = depth.numel(), rows.shape[0], prepared.D, prepared.HW, prepared.H
         d.layout, d.feat_dtype, d.flags = _lib.LAYOUT_B_C_CELLS, _lib.DTYPE_F32, _lib.PLAN_ALL
         out = torch.empty((B, C, 1, 128, 128), dtype=torch.float32, device=dev)
         _lib.check(lib.rcb_bev_pool_v2_fwd(ctypes.byref(d), _lib.ptr(depth), _lib.ptr(rows),

@@ -95,6 +95,7 @@ typedef struct {
   int n_pixels;    /* feat rows      = B*N*H*W                                                    */
   int D;           /* depth bins      } describe the frustum; needed only for RCB_PLAN_STRUCTURED */
   int HW;          /* H*W per camera  }                                                           */
+  int H;           /* feature rows per camera (0 = unknown); lets the backward walk pixel columns   */
   int layout;      /* RCB_LAYOUT_* of `out` / `out_grad`                                          */
   int feat_dtype;  /* RCB_DTYPE_* of `feat` (depth, out and all gradients are float32)            */
   int flags;       /* RCB_PLAN_* bits known to hold for these ranks                               */

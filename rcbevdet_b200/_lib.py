@@ -26,7 +26,7 @@ class PrepareDesc(ctypes.Structure):
 class PoolDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in
                 ("n_points", "n_intervals", "C", "B", "Z", "Y", "X", "n_depth", "n_pixels", "D", "HW",
-                 "layout", "feat_dtype", "flags")]
+                 "H", "layout", "feat_dtype", "flags")]
 
 
 class RadarDesc(ctypes.Structure):

@@ -69,9 +69,9 @@ def _pool_desc(depth, rows, ranks_depth, interval_lengths, bev_feat_shape, layou
     d.B, d.Z, d.Y, d.X = B, Z, Y, X
     d.n_depth, d.n_pixels = depth.numel(), rows.shape[0]
     if depth.dim() == 5 and depth.shape[0] * depth.shape[1] * depth.shape[3] * depth.shape[4] == rows.shape[0]:
-        d.D, d.HW = depth.shape[2], depth.shape[3] * depth.shape[4]
+        d.D, d.HW, d.H = depth.shape[2], depth.shape[3] * depth.shape[4], depth.shape[3]
     else:
-        d.D, d.HW = 0, 0
+        d.D, d.HW, d.H = 0, 0, 0
     d.layout, d.feat_dtype, d.flags = layout, _DTYPES[rows.dtype], 0
     return d
 

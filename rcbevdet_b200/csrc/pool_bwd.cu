@@ -72,6 +72,7 @@ struct BwdPixelParams {
   float *depth_grad;
   float *feat_grad;
   int n_pixels, D, HW, DHW, C4;
+  int H, W;  // 0 when unknown (then pixels are walked in memory order)
 };
 
 // kQ = 128-bit quads per lane (C <= 128*kQ)
@@ -179,6 +180,10 @@ __global__ void __launch_bounds__(256, 3) k_pool_bwd_pixels16(BwdPixelParams p) 
   const char *og = reinterpret_cast<const char *>(p.out_grad_rows);
   const char *feat = static_cast<const char *>(p.feat);
   for (int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pair * 2 < p.n_pixels; pair += warps) {
+    // The two halves of a warp hold horizontally adjacent pixels: their depth / point_cell /
+    // depth_grad words share 32-byte sectors.  (Walking pixel columns instead would let both halves
+    // hit the same out_grad rows, but measured 20 % slower: those strided 4-byte accesses then
+    // waste 7/8 of every sector.)
     const int pix = pair * 2 + half;
     const bool live = pix < p.n_pixels;
     const int pix_c = live ? pix : p.n_pixels - 1;
@@ -344,6 +349,8 @@ extern "C" int rcb_bev_pool_v2_bwd(const rcb_pool_desc *d, const float *out_grad
     p.out_grad_rows = og_rows, p.depth = depth, p.feat = feat, p.point_cell = point_cell;
     p.depth_grad = depth_grad, p.feat_grad = feat_grad;
     p.n_pixels = d->n_pixels, p.D = d->D, p.HW = d->HW, p.DHW = d->D * d->HW, p.C4 = d->C / 4;
+    p.H = d->H > 0 && d->HW % d->H == 0 ? d->H : 1;
+    p.W = d->HW / p.H;
     switch (d->feat_dtype) {
       case RCB_DTYPE_F32: return launch_pixels<float>(p, sms, s);
       case RCB_DTYPE_BF16: return launch_pixels<__nv_bfloat16>(p, sms, s);

@@ -43,7 +43,7 @@ class PreparedRanks:
     """Device-resident result of the prepare pipeline, before any host read-back."""
 
     __slots__ = ("ranks_bev", "ranks_depth", "ranks_feat", "interval_starts", "interval_lengths",
-                 "point_cell", "cell_start", "counts", "grid", "B", "D", "HW", "P", "n_cells")
+                 "point_cell", "cell_start", "counts", "grid", "B", "D", "HW", "H", "P", "n_cells")
 
 
 def prepare_async(coor, grid_lower_bound, grid_interval, grid_size):
@@ -82,7 +82,7 @@ def prepare_async(coor, grid_lower_bound, grid_interval, grid_size):
         _lib.ptr(r.point_cell), _lib.ptr(r.cell_start), _lib.ptr(r.counts), _lib.ptr(ws), ws_bytes,
         dev.index, _lib.stream_ptr(dev)), "rcb_voxel_pooling_prepare_v2")
     r.grid = (gz, gy, gx)
-    r.B, r.D, r.HW, r.P, r.n_cells = desc.B, desc.D, desc.H * desc.W, P, n_cells
+    r.B, r.D, r.HW, r.H, r.P, r.n_cells = desc.B, desc.D, desc.H * desc.W, desc.H, P, n_cells
     return r
 
 

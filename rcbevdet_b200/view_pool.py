@@ -29,7 +29,7 @@ class _ViewPool(torch.autograd.Function):
         d.n_points, d.n_intervals, d.C = prepared.P, 0, C   # upper bounds; the tile kernel reads the CSR
         d.B, d.Z, d.Y, d.X = prepared.B, gz, gy, gx
         d.n_depth, d.n_pixels = depth_c.numel(), rows.shape[0]
-        d.D, d.HW = prepared.D, prepared.HW
+        d.D, d.HW, d.H = prepared.D, prepared.HW, prepared.H
         d.layout, d.feat_dtype, d.flags = _lib.LAYOUT_B_C_CELLS, _bp._DTYPES[rows.dtype], _lib.PLAN_ALL
         if d.n_depth != prepared.P or d.n_pixels * d.D != d.n_depth:
             raise ValueError("depth / feat shapes do not match the frustum that `coor` describes")

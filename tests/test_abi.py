@@ -42,7 +42,7 @@ def test_python_binding_covers_every_symbol():
 def test_struct_layouts_match_header():
     from rcbevdet_b200 import _lib
     assert ctypes.sizeof(_lib.PrepareDesc) == 5 * 4 + 9 * 4
-    assert ctypes.sizeof(_lib.PoolDesc) == 14 * 4
+    assert ctypes.sizeof(_lib.PoolDesc) == 15 * 4
     assert ctypes.sizeof(_lib.RadarDesc) == 6 * 4
 
 
