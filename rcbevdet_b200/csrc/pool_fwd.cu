@@ -113,7 +113,13 @@ __device__ __forceinline__ float4 accumulate_range(const StagePoint *__restrict_
 // kC4 > 0: channels/4 known at compile time; 0: run time (C4 even).  blockDim.x == kGroups * C4,
 // i.e. C4 / 2 warps, and every warp combines / writes two 128-bit channel quads of all 32 cells.
 template <typename FeatT, int kC4>
-__global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ? 3 : 2) : 1)
+#ifndef RCB_FWD_MINCTAS
+#define RCB_FWD_MINCTAS 3
+#endif
+#ifndef RCB_FWD_UNROLL
+#define RCB_FWD_UNROLL 8
+#endif
+__global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ? RCB_FWD_MINCTAS : 2) : 1)
     k_pool_fwd_tile(FwdTileParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C4 = kC4 ? kC4 : p.C4;
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ?
     // ---- items round-robin over the lane-groups ---------------------------------------------
     const int n_items = cell_item0[32];
     for (int it = group; it < n_items; it += kGroups) {
-      const float4 acc = accumulate_range<FeatT, 8>(stage, feat_q, item_lo[it], item_hi[it]);
+      const float4 acc = accumulate_range<FeatT, RCB_FWD_UNROLL>(stage, feat_q, item_lo[it], item_hi[it]);
       *reinterpret_cast<float4 *>(part + (size_t)it * pitch + q * 4) = acc;
     }
     __syncthreads();

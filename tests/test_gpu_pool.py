@@ -247,3 +247,59 @@ def test_hires_geometry_small_batch():
     lo, iv, sz = rig.grid_tensors(grid)
     bev = rcb.voxel_pooling_v2(coor.cuda(), depth.cuda(), feat.cuda(), lo, iv, sz, collapse_z=False)
     _close(bev, oracle.to_bczyx(want), RTOL32, "hires fwd")
+
+
+def test_temporal_frames_folded_into_batch():
+    """BASELINE config 3: the frames of a 4D sample are independent poolings (bevdet_rc.py:756-776),
+    so T frames can be folded into the batch dimension of ONE launch.  The folded result must equal
+    the per-frame results bit for bit, and match the oracle."""
+    import rcbevdet_b200 as rcb
+    from rcbevdet_b200 import rig
+    B, T = 2, 3
+    grid = rig.R50_GRID
+    motion = rig.temporal_motion(B, T, seed=3)                       # (B*T, 3) ego steps per frame
+    calib = rig.camera_rig(B * T, input_size=(128, 352), frame_motion=motion)
+    coor = rig.lidar_coor(calib, [1.0, 60.0, 2.0], (128, 352), 16)
+    _, N, D, H, W, _ = coor.shape
+    depth, feat = rig.pooling_inputs(B * T, N, D, H, W, 80, seed=8)
+    lo, iv, sz = rig.grid_tensors(grid)
+    folded = rcb.voxel_pooling_v2(coor.cuda(), depth.cuda(), feat.cuda(), lo, iv, sz)
+    assert folded.shape == (B * T, 80, 128, 128)
+    for f in range(B * T):
+        one = rcb.voxel_pooling_v2(coor[f:f + 1].cuda(), depth[f:f + 1].cuda(), feat[f:f + 1].cuda(), lo, iv, sz)
+        assert torch.equal(one[0], folded[f]), f"frame {f}"
+    ranks, shape, feat_rows, want = _oracle_pool(coor, depth, feat, grid)
+    _close(folded, oracle.to_bczyx(want)[:, :, 0], RTOL32, "folded frames vs oracle")
+    # frames really differ (ego motion moved the frustum)
+    assert not torch.equal(folded[0], folded[1])
+
+
+def test_hires_full_size_properties():
+    """BASELINE config 5 at full size (56x100 features, D=118, 256x256 BEV, B=2; ~8 M points):
+    integer outputs against the C oracle, plus size-independent properties of the pooled tensor."""
+    import rcbevdet_b200 as rcb
+    from rcbevdet_b200 import rig
+    grid = rig.HIRES_GRID
+    B = 2
+    coor = rig.lidar_coor(rig.camera_rig(B, input_size=rig.HIRES_INPUT), grid["depth"], rig.HIRES_INPUT, 16)
+    _, N, D, H, W, _ = coor.shape
+    assert (D, H, W) == (118, 56, 100)
+    lo, iv, sz = rig.grid_tensors(grid)
+    got = rcb.voxel_pooling_prepare_v2(coor.cuda(), lo, iv, sz)
+    want = oracle.voxel_pooling_prepare_v2_c(coor.numpy(), lo.numpy(), iv.numpy(), sz.numpy(), threads=8)
+    for g, w in zip(got, want):
+        assert np.array_equal(g.cpu().numpy(), w)
+    rb, rd, rf, st, ln = got
+    assert int(ln.max()) > 512                      # exercises the CTA sort tier on real geometry
+    assert bool((rb[1:] >= rb[:-1]).all())
+    # linearity in depth and a checksum identity: sum over cells of out == sum over kept points of w * feat
+    depth, feat = rig.pooling_inputs(B, N, D, H, W, 16, seed=2)
+    d, f = depth.cuda(), feat.cuda()
+    shape = (B, 1, 256, 256, 16)
+    fv = f.permute(0, 1, 3, 4, 2)
+    o1 = rcb.bev_pool_v2(d, fv, rd, rf, rb, shape, st, ln)
+    o2 = rcb.bev_pool_v2(2.0 * d, fv, rd, rf, rb, shape, st, ln)
+    assert torch.allclose(o2, 2.0 * o1, rtol=1e-6, atol=0)
+    rows = fv.reshape(-1, 16).double()
+    total = (d.flatten()[rd.long()].double()[:, None] * rows[rf.long()]).sum(0)
+    assert torch.allclose(o1.double().sum(dim=(0, 2, 3, 4)), total, rtol=1e-6)

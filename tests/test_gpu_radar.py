@@ -65,3 +65,39 @@ def test_empty_input_gives_zeros():
     f, h, hf = rcb.radar_rcs_scatter(z(0, 8), z(0, 7), z(0, 4, dt=torch.int32), 2, 16, 16)
     assert f.shape == (2, 8, 16, 16) and float(f.abs().max()) == 0 and float(h.abs().max()) == 0
     assert float(hf.abs().max()) == 0
+
+
+@pytest.mark.parametrize("ny", [128, 512])
+def test_config4_full_size_properties_and_timing(ny, capsys):
+    """BASELINE config 4 (B=8, 5 sweeps x 5 radars x 125 points per sample) on the 128x128 grid and
+    on the shipped 512x512 pillar grid: exact scatter identities at full size + a timing line."""
+    import rcbevdet_b200 as rcb
+    from rcbevdet_b200 import rig
+    B = 8
+    pf, rc, co = rig.radar_pillars(B, ny, ny, points_per_sample=3125, seed=11)
+    pf, rc, co = pf.cuda(), rc.cuda(), co.cuda()
+    f, h, hf = rcb.radar_rcs_scatter(pf, rc, co, B, ny, ny)
+    # features: exactly the pillar rows at the pillar cells, zero elsewhere
+    picked = f[co[:, 0].long(), :, co[:, 2].long(), co[:, 3].long()]
+    assert torch.equal(picked, pf)
+    assert int((f != 0).sum()) == int((pf != 0).sum())
+    # heat-map: 1.0 exactly at every pillar centre (Gaussian peak), within [0, 1] everywhere
+    assert float(h[co[:, 0].long(), co[:, 2].long(), co[:, 3].long()].min()) == 1.0
+    assert float(h.min()) >= 0.0 and float(h.max()) == 1.0
+    # heatmap_feat holds RCS values only where the heat-map is covered
+    assert bool(((hf[:, 0] != 0) <= (h > 0)).all())
+    # idempotence / determinism
+    f2, h2, hf2 = rcb.radar_rcs_scatter(pf, rc, co, B, ny, ny)
+    assert torch.equal(f, f2) and torch.equal(h, h2) and torch.equal(hf, hf2)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(20):
+        rcb.radar_rcs_scatter(pf, rc, co, B, ny, ny)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 20
+    out_bytes = B * ny * ny * (64 + 2) * 4 + pf.numel() * 4 + rc.numel() * 4 + co.numel() * 4
+    with capsys.disabled():
+        print(f"\n[timing] radar RCS scatter B=8 V={pf.shape[0]} grid {ny}x{ny}: {ms * 1e3:.1f} us, "
+              f"{out_bytes / ms / 1e6:.0f} GB/s algorithmic ({B / ms * 1e3:.0f} samples/s)")

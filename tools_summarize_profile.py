@@ -60,6 +60,7 @@ with open(os.path.join(out_dir, f"{tag}_ncu_kernels.md"), "w") as f:
     f.write("\n".join(lines) + "\n")
 
 # DRAM traffic per launch, grouped by bench.py stage
+# bench.py's roofline is quoted on ONE kernel: "fwd" = k_pool_fwd_tile, "bwd" = k_pool_bwd_pixels16
 stage_of = {"k_point_cells": "prepare", "k_scan_cells": "prepare", "k_scatter_points": "prepare",
             "k_sort_cells_warp": "prepare", "k_sort_cells_cta": "prepare", "k_pool_fwd_tile": "fwd",
             "k_pool_bwd_pixels16": "bwd", "k_pool_bwd_pixels": "bwd"}
@@ -75,12 +76,6 @@ for name, d in seen.items():
         continue
     if st:
         traffic[st] = traffic.get(st, 0) + int(b)
-# the out_grad transpose belongs to the bwd stage: second k_planes_to_rows launch is the big one
-big = [to_bytes(d[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) +
-       to_bytes(d[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
-       for d in data if "k_planes_to_rows" in d[idx["Kernel Name"]]]
-if big:
-    traffic["bwd"] = traffic.get("bwd", 0) + int(max(big))
 traffic["_per_kernel"] = per_kernel
 traffic["_source"] = f"profiles/{tag}_ncu_kernels.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
 with open(os.path.join(out_dir, "traffic.json"), "w") as f:
