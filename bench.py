@@ -159,7 +159,7 @@ def run_ours(args):
     stream = torch.cuda.current_stream(dev)
 
     stage_names = ("prepare", "feat_rows", "fwd", "og_rows", "bwd")
-    n_kernels = {"prepare": 6, "feat_rows": 1, "fwd": 1, "og_rows": 1, "bwd": 1}
+    n_kernels = {"prepare": 5, "feat_rows": 1, "fwd": 1, "og_rows": 1, "bwd": 1}
     stage_events = {s: [] for s in stage_names}
 
     def step(i, record):
@@ -182,8 +182,7 @@ def run_ours(args):
         _lib.check(lib.rcb_bev_pool_v2_fwd(ctypes.byref(d), _lib.ptr(depth), _lib.ptr(rows),
                                            _lib.ptr(prepared.ranks_depth), _lib.ptr(prepared.ranks_feat),
                                            _lib.ptr(prepared.ranks_bev), None, None, _lib.ptr(prepared.cell_start),
-                                           _lib.ptr(prepared.tile_work), _lib.ptr(out), dev.index,
-                                           _lib.stream_ptr(dev)), "fwd")   # row F
+                                           _lib.ptr(out), dev.index, _lib.stream_ptr(dev)), "fwd")   # row F
         if record:
             ev[3].record(stream)
         # backward = out_grad (B,C,cells) -> channels-last rows (bev_pool.py:69), then the gradient kernel
@@ -252,8 +251,7 @@ def run_ours(args):
             _lib.check(lib.rcb_bev_pool_v2_fwd(ctypes.byref(d), _lib.ptr(depth), _lib.ptr(rows),
                                                _lib.ptr(prepared.ranks_depth), _lib.ptr(prepared.ranks_feat),
                                                _lib.ptr(prepared.ranks_bev), None, None,
-                                               _lib.ptr(prepared.cell_start), _lib.ptr(prepared.tile_work),
-                                               _lib.ptr(outs[k % 4]), dev.index,
+                                               _lib.ptr(prepared.cell_start), _lib.ptr(outs[k % 4]), dev.index,
                                                _lib.stream_ptr(dev)), "fwd")
         e1.record(stream)
         torch.cuda.synchronize(dev)

@@ -121,7 +121,7 @@ int rcb_pool_build_cellmap(const rcb_pool_desc *d, const int *ranks_bev, const i
  * Forward.  depth: float32 [n_depth]; feat: [n_pixels, C] channels last, `feat_dtype`;
  * out: float32 [B*Z*Y*X*C] in `layout`, fully written on return (the reference needs it
  * pre-zeroed, bev_pool.py:27, and a permute copy afterwards, bev_pool.py:91 -- neither here).
- *   cell_start != NULL (ranks with RCB_PLAN_SORTED_CELLS): tile kernel, one pass (tile_work optional).
+ *   cell_start != NULL (ranks with RCB_PLAN_SORTED_CELLS): tile kernel, one pass.
  *   cell_start == NULL: general path for arbitrary ranks (memset + one warp per interval).
  * Argument order of the rank arrays follows bev_pool_v2_forward (bev_pool.cpp:30-38):
  * interval_lengths BEFORE interval_starts.
@@ -129,16 +129,7 @@ int rcb_pool_build_cellmap(const rcb_pool_desc *d, const int *ranks_bev, const i
 int rcb_bev_pool_v2_fwd(const rcb_pool_desc *d, const float *depth, const void *feat,
                         const int *ranks_depth, const int *ranks_feat, const int *ranks_bev,
                         const int *interval_lengths, const int *interval_starts,
-                        const int *cell_start, const int *tile_work, float *out, int device,
-                        rcb_stream_t stream);
-
-/* Optional work list for the tile kernel (depends on cell_start only, so it can be cached with
- * the ranks): patches holding more than one staging round of points are cut into row bands that
- * separate CTAs pool concurrently, and are scheduled first.  tile_work == NULL in
- * rcb_bev_pool_v2_fwd means one CTA per patch, centre-first order. */
-size_t rcb_pool_tile_work_bytes(const rcb_pool_desc *d);
-int rcb_pool_plan_tiles(const rcb_pool_desc *d, const int *cell_start, int *tile_work, int device,
-                        rcb_stream_t stream);
+                        const int *cell_start, float *out, int device, rcb_stream_t stream);
 
 /*
  * Backward (bev_pool.cpp:74-104).  out_grad float32 in `layout`; depth_grad float32 [n_depth];

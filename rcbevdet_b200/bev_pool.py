@@ -106,8 +106,7 @@ def _forward(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, in
     _lib.check(_lib.lib().rcb_bev_pool_v2_fwd(
         ctypes.byref(desc), _lib.ptr(depth), _lib.ptr(rows), _lib.ptr(ranks_depth), _lib.ptr(ranks_feat),
         _lib.ptr(ranks_bev), _lib.ptr(interval_lengths), _lib.ptr(interval_starts),
-        _lib.ptr(plan.cell_start if plan.sorted_cells else None),
-        _lib.ptr(plan.tile_work if plan.sorted_cells else None), _lib.ptr(out), dev.index,
+        _lib.ptr(plan.cell_start if plan.sorted_cells else None), _lib.ptr(out), dev.index,
         _lib.stream_ptr(dev)), "rcb_bev_pool_v2_fwd")
     saved = (depth, rows, ranks_depth, ranks_feat, ranks_bev)
     return out, saved, desc, plan

@@ -34,7 +34,6 @@ constexpr int kStagePerThread = 4;            // points staged per thread and ro
 constexpr int kMinItem = 32;
 constexpr int kMaxItems = kTileCells + kGroups;
 constexpr int kFwdTableBytes = 1024;
-constexpr int kPlanRoundPoints = 1280;        // patches above this are cut into row bands (k_plan_tiles)
 
 struct FwdTileParams {
   const float *depth;
@@ -42,8 +41,6 @@ struct FwdTileParams {
   const int *ranks_depth;
   const int *ranks_feat;
   const int *cell_start;
-  const int *tile_work;  // optional work list (see k_plan_tiles); NULL = one CTA per patch
-  int work_cap;
   float *out;
   int C, C4;
   int X, R;              // cells per row, rows per sample (Z*Y)
@@ -84,18 +81,8 @@ __device__ __forceinline__ void fma_row(float4 &acc, const float4 v, const float
 }
 
 #ifdef RCB_PROFILE_PHASES
-__device__ long long g_fwd_prof[16384 * 8];
-__device__ __forceinline__ long long rcb_gtime() {
-  long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ int rcb_smid() {
-  int v;
-  asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
-  return v;
-}
-#define RCB_T(k) if (threadIdx.x == 0 && blockIdx.x < 16384) g_fwd_prof[blockIdx.x * 8 + (k)] = rcb_gtime();
+__device__ long long g_fwd_prof[8192 * 8];
+#define RCB_T(k) if (threadIdx.x == 0 && blockIdx.x < 8192) g_fwd_prof[blockIdx.x * 8 + (k)] = clock64();
 #else
 #define RCB_T(k)
 #endif
@@ -152,32 +139,16 @@ __global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ?
 
   RCB_T(0)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
-  int b, tx_i, tr_i, row0 = 0, rows = kTileY;
-  if (p.tile_work != nullptr) {
-    // work list: heavy patches first, cut into row bands that separate CTAs pool concurrently
-    const int n_heavy = __ldg(p.tile_work), n_light = __ldg(p.tile_work + 1);
-    int e;
-    if ((int)blockIdx.x < n_heavy) e = __ldg(p.tile_work + 2 + blockIdx.x);
-    else if ((int)blockIdx.x - n_heavy < n_light) e = __ldg(p.tile_work + p.work_cap - 1 - ((int)blockIdx.x - n_heavy));
-    else return;
-    rows = (e & 3) + 1, row0 = (e >> 2) & 3;
-    int t = e >> 4;
-    tx_i = t % p.tiles_x;
-    t /= p.tiles_x;
-    tr_i = t % p.tiles_r;
-    b = t / p.tiles_r;
-  } else {
-    // Launch order: patches nearest the grid centre first, samples interleaved.  Point density
-    // peaks around the ego vehicle (a patch there holds ~8x the average), so the long patches start
-    // at once instead of forming the kernel's tail.  Any order is correct; this one is a heuristic.
-    int t = blockIdx.x;
-    b = t % p.B;
-    t /= p.B;
-    tx_i = zigzag_from_centre(t % p.tiles_x, p.tiles_x);
-    tr_i = zigzag_from_centre(t / p.tiles_x, p.tiles_r);
-  }
-  const int x0 = tx_i * kTileX, r0 = tr_i * kTileY + row0;
-  const int nx = min(kTileX, p.X - x0), nr = min(rows, p.R - r0);
+  // Launch order: patches nearest the grid centre first, samples interleaved.  Point density
+  // peaks around the ego vehicle (a patch there holds ~8x the average), so the long patches start
+  // at once instead of forming the kernel's tail.  Any order is correct; this one is a heuristic.
+  int t = blockIdx.x;
+  const int b = t % p.B;
+  t /= p.B;
+  const int tx_i = zigzag_from_centre(t % p.tiles_x, p.tiles_x);
+  const int tr_i = zigzag_from_centre(t / p.tiles_x, p.tiles_r);
+  const int x0 = tx_i * kTileX, r0 = tr_i * kTileY;
+  const int nx = min(kTileX, p.X - x0), nr = min(kTileY, p.R - r0);
   const int cell_base = b * p.cells_per_sample;
 
   // ---- patch geometry, by warp 0: lane <-> cell ----------------------------------------------
@@ -208,7 +179,7 @@ __global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ?
   RCB_T(1)
   const int total = seg_off[kTileY];
 #ifdef RCB_PROFILE_PHASES
-  if (threadIdx.x == 0 && blockIdx.x < 16384) g_fwd_prof[blockIdx.x * 8 + 7] = total, g_fwd_prof[blockIdx.x * 8 + 6] = rcb_smid();
+  if (threadIdx.x == 0 && blockIdx.x < 8192) g_fwd_prof[blockIdx.x * 8 + 7] = total;
 #endif
 
   const int group = tid / C4, q = tid - group * C4;
@@ -312,43 +283,6 @@ __global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ?
       st_stream_f32(d4 + 3 * (size_t)p.cells_per_sample, racc[k].w);
     }
   }
-  RCB_T(5)
-}
-
-// ---------------------------------------------------------------------------------------------
-// Work list for the tile kernel (geometry only: depends on cell_start, not on depth / context).
-// Point density is very uneven (a patch next to the ego vehicle holds ~8x the mean), and a CTA
-// walks its patch in rounds, so the few heavy patches used to be the kernel's critical path.
-// Here every patch holding more than one round of points is cut into 2 or 4 row bands, each its
-// own CTA, and those entries are placed at the FRONT of the list (light patches fill it from the
-// back), so they are scheduled first.  work[0] = heavy entries, work[1] = light entries;
-// entry = patch << 4 | first_row << 2 | (rows - 1).
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-    k_plan_tiles(const int *__restrict__ cell_start, int n_tiles, int tiles_x, int tiles_r, int X, int R,
-                 int cells_per_sample, int round_points, int *__restrict__ work, int work_cap) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_tiles) return;
-  int u = t;
-  const int tx_i = u % tiles_x;
-  u /= tiles_x;
-  const int tr_i = u % tiles_r;
-  const int b = u / tiles_r;
-  const int x0 = tx_i * kTileX, r0 = tr_i * kTileY;
-  const int nx = min(kTileX, X - x0), nr = min(kTileY, R - r0);
-  int total = 0;
-  for (int r = 0; r < nr; ++r) {
-    const int c = b * cells_per_sample + (r0 + r) * X + x0;
-    total += __ldg(cell_start + c + nx) - __ldg(cell_start + c);
-  }
-  if (total > round_points && nr == kTileY) {
-    const int bands = total > 2 * round_points ? 4 : 2, rows = kTileY / bands;
-    const int at = atomicAdd(work, bands);
-    for (int k = 0; k < bands; ++k) work[2 + at + k] = (t << 4) | ((k * rows) << 2) | (rows - 1);
-  } else {
-    const int at = atomicAdd(work + 1, 1);
-    work[work_cap - 1 - at] = (t << 4) | (nr - 1 > 0 ? nr - 1 : 0);
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -401,9 +335,7 @@ static int launch_tile_c4(const rcb_pool_desc *d, FwdTileParams &p, cudaStream_t
   const size_t smem = fwd_tile_smem_bytes(p.C);
   RCB_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd_tile<FeatT, kC4>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  long long grid = (long long)d->B * p.tiles_r * p.tiles_x;
-  if (p.tile_work != nullptr)  // every patch once + at most 3 extra bands per heavy patch
-    grid += 3 * min(grid, (long long)(d->n_points / kPlanRoundPoints) + 1);
+  const long long grid = (long long)d->B * p.tiles_r * p.tiles_x;
   k_pool_fwd_tile<FeatT, kC4><<<(unsigned)grid, threads, smem, s>>>(p);
   RCB_LAUNCH_CHECK();
   return RCB_OK;
@@ -450,9 +382,8 @@ using namespace rcb;
 extern "C" int rcb_bev_pool_v2_fwd(const rcb_pool_desc *d, const float *depth, const void *feat,
                                    const int *ranks_depth, const int *ranks_feat,
                                    const int *ranks_bev, const int *interval_lengths,
-                                   const int *interval_starts, const int *cell_start,
-                                   const int *tile_work, float *out, int device,
-                                   rcb_stream_t stream) {
+                                   const int *interval_starts, const int *cell_start, float *out,
+                                   int device, rcb_stream_t stream) {
   int rc = check_pool_desc(d);
   if (rc != RCB_OK) return rc;
   if (!out) return RCB_ERR_ARG;
@@ -470,8 +401,6 @@ extern "C" int rcb_bev_pool_v2_fwd(const rcb_pool_desc *d, const float *depth, c
     FwdTileParams p;
     p.depth = depth, p.feat = feat, p.ranks_depth = ranks_depth, p.ranks_feat = ranks_feat;
     p.cell_start = cell_start, p.out = out;
-    p.tile_work = tile_work;
-    p.work_cap = 2 + 4 * d->B * ceil_div(d->X, kTileX) * ceil_div(d->Z * d->Y, kTileY);
     p.C = d->C, p.C4 = d->C / 4;
     p.X = d->X, p.R = d->Z * d->Y;
     p.tiles_x = ceil_div(p.X, kTileX), p.tiles_r = ceil_div(p.R, kTileY);
@@ -506,33 +435,4 @@ extern "C" int rcb_bev_pool_v2_fwd(const rcb_pool_desc *d, const float *depth, c
 extern "C" int rcb_debug_fwd_prof(long long *host, int n) {
   return (int)cudaMemcpyFromSymbol(host, rcb::g_fwd_prof, sizeof(long long) * n);
 }
-extern "C" int rcb_debug_fwd_prof_reset() {
-  void *p = nullptr;
-  cudaGetSymbolAddress(&p, rcb::g_fwd_prof);
-  return (int)cudaMemset(p, 0, sizeof(long long) * 16384 * 8);
-}
 #endif
-
-extern "C" size_t rcb_pool_tile_work_bytes(const rcb_pool_desc *d) {
-  if (check_pool_desc(d) != RCB_OK) return 0;
-  return (size_t)(2 + 4 * (size_t)d->B * ceil_div(d->X, kTileX) * ceil_div(d->Z * d->Y, kTileY)) * sizeof(int);
-}
-
-extern "C" int rcb_pool_plan_tiles(const rcb_pool_desc *d, const int *cell_start, int *tile_work, int device,
-                                   rcb_stream_t stream) {
-  int rc = check_pool_desc(d);
-  if (rc != RCB_OK) return rc;
-  if (!cell_start || !tile_work) return RCB_ERR_ARG;
-  DeviceGuard guard(device);
-  if (guard.err) return guard.err;
-  cudaStream_t s = (cudaStream_t)stream;
-  const int tiles_x = ceil_div(d->X, kTileX), tiles_r = ceil_div(d->Z * d->Y, kTileY);
-  const int n_tiles = d->B * tiles_x * tiles_r;
-  const int cap = 2 + 4 * n_tiles;
-  if ((long long)n_tiles >= (1ll << 27)) return RCB_ERR_UNSUPPORTED;
-  RCB_CUDA_TRY(cudaMemsetAsync(tile_work, 0, 2 * sizeof(int), s));
-  k_plan_tiles<<<ceil_div(n_tiles, 256), 256, 0, s>>>(cell_start, n_tiles, tiles_x, tiles_r, d->X, d->Z * d->Y,
-                                                      d->Z * d->Y * d->X, kPlanRoundPoints, tile_work, cap);
-  RCB_LAUNCH_CHECK();
-  return RCB_OK;
-}

@@ -25,14 +25,12 @@ class PoolPlan:
     unless SORTED_CELLS).  point_cell: int32 [n_depth] BEV cell of each depth element, -1 if
     unused (None unless STRUCTURED).  D / HW describe the frustum when STRUCTURED."""
 
-    __slots__ = ("flags", "cell_start", "point_cell", "tile_work", "D", "HW", "n_cells", "n_depth", "keys", "hold")
+    __slots__ = ("flags", "cell_start", "point_cell", "D", "HW", "n_cells", "n_depth", "keys", "hold")
 
-    def __init__(self, flags, cell_start, point_cell, D, HW, n_cells, n_depth, keys=None, hold=None,
-                 tile_work=None):
+    def __init__(self, flags, cell_start, point_cell, D, HW, n_cells, n_depth, keys=None, hold=None):
         self.flags = int(flags)
         self.cell_start = cell_start
         self.point_cell = point_cell
-        self.tile_work = tile_work
         self.D = int(D)
         self.HW = int(HW)
         self.n_cells = int(n_cells)
@@ -82,17 +80,6 @@ def lookup(ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths
     return plan
 
 
-def plan_tiles(desc, cell_start):
-    """Work list of the forward tile kernel for this CSR (heavy patches split and scheduled first)."""
-    lib = _lib.lib()
-    dev = cell_start.device
-    n = lib.rcb_pool_tile_work_bytes(ctypes.byref(desc))
-    work = torch.empty(max(n // 4, 2), dtype=torch.int32, device=dev)
-    _lib.check(lib.rcb_pool_plan_tiles(ctypes.byref(desc), _lib.ptr(cell_start), _lib.ptr(work), dev.index,
-                                       _lib.stream_ptr(dev)), "rcb_pool_plan_tiles")
-    return work
-
-
 def derive(desc, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths):
     """Validate foreign ranks on the device (one flag read-back) and cache the result."""
     dev = ranks_depth.device if ranks_depth.numel() else ranks_bev.device
@@ -117,13 +104,12 @@ def derive(desc, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_l
         _lib.check(lib.rcb_pool_build_cellmap(ctypes.byref(desc), _lib.ptr(ranks_bev),
                                               _lib.ptr(interval_starts), _lib.ptr(cell_start), dev.index, st),
                    "rcb_pool_build_cellmap")
-    tile_work = plan_tiles(desc, cell_start) if cell_start is not None else None
     if not flags & _lib.PLAN_STRUCTURED:
         point_cell = None
     tensors = (ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths)
     keys = tuple(_key(t) for t in tensors)
     plan = PoolPlan(flags, cell_start, point_cell, desc.D, desc.HW, n_cells, desc.n_depth, keys=keys,
-                    hold=tensors, tile_work=tile_work)  # holding the tensors keeps their addresses from being reused
+                    hold=tensors)  # holding the tensors keeps their addresses from being reused
     with _cache_lock:
         _cache[(keys, n_cells, desc.n_depth)] = plan
         while len(_cache) > _CACHE_MAX:

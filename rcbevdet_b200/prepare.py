@@ -43,7 +43,7 @@ class PreparedRanks:
     """Device-resident result of the prepare pipeline, before any host read-back."""
 
     __slots__ = ("ranks_bev", "ranks_depth", "ranks_feat", "interval_starts", "interval_lengths",
-                 "point_cell", "cell_start", "tile_work", "counts", "grid", "B", "D", "HW", "H", "P", "n_cells")
+                 "point_cell", "cell_start", "counts", "grid", "B", "D", "HW", "H", "P", "n_cells")
 
 
 def prepare_async(coor, grid_lower_bound, grid_interval, grid_size):
@@ -82,9 +82,6 @@ def prepare_async(coor, grid_lower_bound, grid_interval, grid_size):
         _lib.ptr(r.point_cell), _lib.ptr(r.cell_start), _lib.ptr(r.counts), _lib.ptr(ws), ws_bytes,
         dev.index, _lib.stream_ptr(dev)), "rcb_voxel_pooling_prepare_v2")
     r.grid = (gz, gy, gx)
-    pd = _lib.PoolDesc()
-    pd.n_points, pd.C, pd.B, pd.Z, pd.Y, pd.X = P, 4, desc.B, gz, gy, gx
-    r.tile_work = _plan.plan_tiles(pd, r.cell_start)
     r.B, r.D, r.HW, r.H, r.P, r.n_cells = desc.B, desc.D, desc.H * desc.W, desc.H, P, n_cells
     return r
 
@@ -101,8 +98,7 @@ def voxel_pooling_prepare_v2(coor, grid_lower_bound, grid_interval, grid_size):
         return None, None, None, None, None
     out = (r.ranks_bev[:n_kept], r.ranks_depth[:n_kept], r.ranks_feat[:n_kept],
            r.interval_starts[:n_iv], r.interval_lengths[:n_iv])
-    p = _plan.PoolPlan(_lib.PLAN_ALL, r.cell_start, r.point_cell, r.D, r.HW, r.n_cells, r.P,
-                       tile_work=r.tile_work)
+    p = _plan.PoolPlan(_lib.PLAN_ALL, r.cell_start, r.point_cell, r.D, r.HW, r.n_cells, r.P)
     _plan.attach(p, out[1], out[2], out[0], out[3], out[4])
     return out
 

@@ -37,12 +37,11 @@ class _ViewPool(torch.autograd.Function):
         _lib.check(_lib.lib().rcb_bev_pool_v2_fwd(
             ctypes.byref(d), _lib.ptr(depth_c), _lib.ptr(rows), _lib.ptr(prepared.ranks_depth),
             _lib.ptr(prepared.ranks_feat), _lib.ptr(prepared.ranks_bev), None, None,
-            _lib.ptr(prepared.cell_start), _lib.ptr(prepared.tile_work), _lib.ptr(out), dev.index,
-            _lib.stream_ptr(dev)),
+            _lib.ptr(prepared.cell_start), _lib.ptr(out), dev.index, _lib.stream_ptr(dev)),
             "rcb_bev_pool_v2_fwd")
         ctx.save_for_backward(depth_c, rows, prepared.ranks_depth, prepared.ranks_feat, prepared.ranks_bev)
         plan = _plan.PoolPlan(_lib.PLAN_ALL, prepared.cell_start, prepared.point_cell, prepared.D,
-                              prepared.HW, prepared.n_cells, prepared.P, tile_work=prepared.tile_work)
+                              prepared.HW, prepared.n_cells, prepared.P)
         ctx.rcb = (d, plan, tuple(feat.shape), feat.dtype, tuple(depth.shape), depth.dtype)
         return out
 
