@@ -257,10 +257,12 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         return e0.elapsed_time(e1) / n
 
-    rows32 = bp.feat_rows(sets[0][2].permute(0, 1, 3, 4, 2))
-    variants = {"fwd_f32_rows_ms": round(fwd_only(rows32, _lib.DTYPE_F32), 5),
-                "fwd_bf16_rows_ms": round(fwd_only(rows32.bfloat16(), _lib.DTYPE_BF16), 5),
-                "note": "forward kernel alone, same plan, 4 rotating outputs (inputs L2-warm)"}
+    variants = None
+    if not args.profile:
+        rows32 = bp.feat_rows(sets[0][2].permute(0, 1, 3, 4, 2))
+        variants = {"fwd_f32_rows_ms": round(fwd_only(rows32, _lib.DTYPE_F32), 5),
+                    "fwd_bf16_rows_ms": round(fwd_only(rows32.bfloat16(), _lib.DTYPE_BF16), 5),
+                    "note": "forward kernel alone, same plan, 4 rotating outputs (inputs L2-warm)"}
 
     # ---- end to end through the public API from pinned host buffers --------------------------
     host_sets = [tuple(t.pin_memory() for t in make_inputs(torch, rig, "cpu", B, seed=100 * rank + 10 * s + 1))
@@ -311,8 +313,8 @@ def run_ours(args):
         ev_d2h[(n - 1) % 2].synchronize()
         torch.cuda.synchronize(dev)
 
-    e2e_steps = max(4, min(args.steps, 60))
-    e2e_run(4)
+    e2e_steps = 2 if args.profile else max(4, min(args.steps, 60))
+    e2e_run(2 if args.profile else 4)
     barrier()
     w0 = time.perf_counter()
     e2e_run(e2e_steps)
@@ -471,6 +473,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="timed steps only (no variants, minimal e2e): the command line used under ncu")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
