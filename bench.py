@@ -159,7 +159,7 @@ def run_ours(args):
     stream = torch.cuda.current_stream(dev)
 
     stage_names = ("prepare", "feat_rows", "fwd", "og_rows", "bwd")
-    n_kernels = {"prepare": 5, "feat_rows": 1, "fwd": 1, "og_rows": 1, "bwd": 1}
+    n_kernels = {"prepare": 8, "feat_rows": 1, "fwd": 1, "og_rows": 1, "bwd": 1}
     stage_events = {s: [] for s in stage_names}
 
     def step(i, record):
