@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = os.path.join(ROOT, "gpurun_out", f"prof_{tag}.ncu-rep")
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
