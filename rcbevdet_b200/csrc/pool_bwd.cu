@@ -202,7 +202,11 @@ __global__ void __launch_bounds__(256, 3) k_pool_bwd_pixels16(BwdPixelParams p) 
       fs[j] = Elem<FeatT>::load(frow + (64 * kNQ + 16 * j + l16) * sizeof(FeatT));
       gs[j] = 0.f;
     }
+    // per-lane bases of the quad part and of the scalar tail of an out_grad row, pinned in
+    // registers so that each row address is ONE 32x32+64 multiply-add of the cell index
     const char *og_lane = og + (size_t)l16 * 16;
+    const char *og_tail = og + 256 * kNQ + (size_t)l16 * 4;
+    asm volatile("" : "+l"(og_lane), "+l"(og_tail));
     for (int d0 = 0; d0 < p.D; d0 += 16) {
       const int my_d = d0 + l16;
       int my_cell = -1;
@@ -218,7 +222,8 @@ __global__ void __launch_bounds__(256, 3) k_pool_bwd_pixels16(BwdPixelParams p) 
         const float w = __shfl_sync(kFull, my_w, k, 16);
         float s = 0.f;
         if (cell >= 0) {
-          const char *row = og_lane + (size_t)cell * (kC * 4);
+          const unsigned row_off = (unsigned)cell * (unsigned)(kC * 4);
+          const char *row = og_lane + row_off;
           const float2 ww = make_float2(w, w);
           float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
@@ -235,7 +240,7 @@ __global__ void __launch_bounds__(256, 3) k_pool_bwd_pixels16(BwdPixelParams p) 
 #pragma unroll
           for (int j = 0; j < kNS; ++j) {
             // scalar tail: channel 64*kNQ + 16*j + l16
-            const float g = __ldg(reinterpret_cast<const float *>(row + (256 * kNQ + 64 * j) - 12 * l16));
+            const float g = __ldg(reinterpret_cast<const float *>(og_tail + row_off + 64 * j));
             s = fmaf(g, fs[j], s);
             gs[j] = fmaf(g, w, gs[j]);
           }
