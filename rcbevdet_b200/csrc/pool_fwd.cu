@@ -52,7 +52,7 @@ struct FwdTileParams {
 
 struct __align__(8) StagePoint {
   float w;
-  unsigned row_bytes;  // ranks_feat * C * sizeof(FeatT): byte offset of the context row
+  unsigned row;  // ranks_feat: index of the context row
 };
 
 // i-th element of {c, c-1, c+1, c-2, c+2, ...} clipped to [0, n), c = n / 2
@@ -91,7 +91,8 @@ __device__ long long g_fwd_prof[8192 * 8];
 // reference's order), kUnroll independent 128-bit row loads in flight
 template <typename FeatT, int kUnroll>
 __device__ __forceinline__ float4 accumulate_range(const StagePoint *__restrict__ stage,
-                                                   const char *__restrict__ feat_q, int i, int hi) {
+                                                   const char *__restrict__ feat_q, unsigned row_stride,
+                                                   int i, int hi) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (; i + kUnroll <= hi; i += kUnroll) {
     StagePoint sp[kUnroll];
@@ -99,13 +100,14 @@ __device__ __forceinline__ float4 accumulate_range(const StagePoint *__restrict_
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) sp[u] = stage[i + u];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) v[u] = Row4<FeatT>::load_bytes(feat_q + sp[u].row_bytes);
+    for (int u = 0; u < kUnroll; ++u)
+      v[u] = Row4<FeatT>::load_bytes(feat_q + (size_t)sp[u].row * row_stride);  // one IMAD.WIDE
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) fma_row(acc, v[u], sp[u].w);
   }
   for (; i < hi; ++i) {
     const StagePoint s0 = stage[i];
-    fma_row(acc, Row4<FeatT>::load_bytes(feat_q + s0.row_bytes), s0.w);
+    fma_row(acc, Row4<FeatT>::load_bytes(feat_q + (size_t)s0.row * row_stride), s0.w);
   }
   return acc;
 }
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ?
       for (int k = 0; k < kStagePerThread; ++k) {
         if (g[k] >= 0) {
           StagePoint sp;
-          sp.row_bytes = rf[k] * row_stride;
+          sp.row = rf[k];
           sp.w = ld_stream_f32(p.depth + rd[k]);  // used once per cell: keep it out of L1
           stage[tid + k * blockDim.x] = sp;
         }
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ?
     // ---- items round-robin over the lane-groups ---------------------------------------------
     const int n_items = cell_item0[32];
     for (int it = group; it < n_items; it += kGroups) {
-      const float4 acc = accumulate_range<FeatT, RCB_FWD_UNROLL>(stage, feat_q, item_lo[it], item_hi[it]);
+      const float4 acc = accumulate_range<FeatT, RCB_FWD_UNROLL>(stage, feat_q, row_stride, item_lo[it], item_hi[it]);
       *reinterpret_cast<float4 *>(part + (size_t)it * pitch + q * 4) = acc;
     }
     __syncthreads();
