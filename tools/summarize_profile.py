@@ -61,8 +61,8 @@ with open(os.path.join(out_dir, f"{tag}_ncu_kernels.md"), "w") as f:
 
 # DRAM traffic per launch, grouped by bench.py stage
 # bench.py's roofline is quoted on ONE kernel: "fwd" = k_pool_fwd_tile, "bwd" = k_pool_bwd_pixels16
-stage_of = {"k_point_cells": "prepare", "k_scan_cells": "prepare", "k_scatter_points": "prepare",
-            "k_sort_cells_warp": "prepare", "k_sort_cells_cta": "prepare", "k_pool_fwd_tile": "fwd",
+stage_of = {"k_cells_hist": "prepare", "k_scan_u32": "prepare", "k_radix_scatter": "prepare",
+            "k_radix_hist": "prepare", "k_cell_bounds": "prepare", "k_intervals": "prepare", "k_pool_fwd_tile": "fwd",
             "k_pool_bwd_pixels16": "bwd", "k_pool_bwd_pixels": "bwd"}
 traffic = {}
 per_kernel = {}
