@@ -43,10 +43,51 @@ __global__ void __launch_bounds__(256) k_planes_to_rows(const TIn *__restrict__ 
   }
 }
 
+// fp32 fast path (C % 4 == 0, HW % 4 == 0, 16-byte aligned): one CTA moves 64 consecutive pixels x
+// all C channels with 128-bit global accesses on both sides.  Loads: every channel row contributes
+// 256 contiguous bytes; stores: the 64*C output floats are ONE contiguous run.  The generic kernel
+// above spends ~36 instructions per element on index arithmetic and is issue-bound (ncu: 75 %
+// issue-active at 3.2 TB/s); this one moves four elements per load/store instruction.
+constexpr int kV4Pixels = 64;
+__global__ void __launch_bounds__(256) k_planes_to_rows_v4(const float *__restrict__ src, float *__restrict__ dst,
+                                                           int C, int HW, long long src_img_stride) {
+  extern __shared__ float tile_v4[];  // [kV4Pixels][C + 1]
+  const int P = C + 1;
+  const int img = blockIdx.y;
+  const int hw0 = blockIdx.x * kV4Pixels;
+  const int n_hw = min(kV4Pixels, HW - hw0);  // multiple of 4
+  const float *s = src + (size_t)img * src_img_stride + hw0;
+  const int quads_per_row = n_hw >> 2;
+  for (int f = threadIdx.x; f < C * quads_per_row; f += 256) {
+    const int c = f / quads_per_row, j = f - c * quads_per_row;
+    const float4 v = ld_stream_f4(reinterpret_cast<const float4 *>(s + (size_t)c * HW) + j);
+    float *t = tile_v4 + (4 * j) * P + c;
+    t[0] = v.x, t[P] = v.y, t[2 * P] = v.z, t[3 * P] = v.w;
+  }
+  __syncthreads();
+  float4 *d = reinterpret_cast<float4 *>(dst + ((size_t)img * HW + hw0) * C);
+  const int c_quads = C >> 2;
+  for (int g = threadIdx.x; g < n_hw * c_quads; g += 256) {
+    const int hw = g / c_quads, cq = g - hw * c_quads;
+    const float *t = tile_v4 + hw * P + 4 * cq;
+    st_stream_f4(d + g, make_float4(t[0], t[1], t[2], t[3]));
+  }
+}
+
 int planes_to_rows_launch(const void *src, void *dst, int n_img, int C, int HW,
                           long long src_img_stride, int elem_bytes, cudaStream_t s) {
   if (n_img <= 0 || C <= 0 || HW <= 0) return RCB_OK;
   if (n_img > 65535) return RCB_ERR_UNSUPPORTED;
+  if (elem_bytes == 4 && (C % 4) == 0 && (HW % 4) == 0 && HW >= 2048 && C <= 256 && (src_img_stride % 4) == 0 &&
+      (((uintptr_t)src) % 16) == 0 && (((uintptr_t)dst) % 16) == 0) {
+    const size_t smem = (size_t)kV4Pixels * (C + 1) * 4;
+    if (smem > 48 * 1024)
+      RCB_CUDA_TRY(cudaFuncSetAttribute(k_planes_to_rows_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 g4(ceil_div(HW, kV4Pixels), n_img);
+    k_planes_to_rows_v4<<<g4, 256, smem, s>>>((const float *)src, (float *)dst, C, HW, src_img_stride);
+    RCB_LAUNCH_CHECK();
+    return RCB_OK;
+  }
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), n_img);
   if (elem_bytes == 4)
     k_planes_to_rows<float, float><<<grid, 256, 0, s>>>((const float *)src, (float *)dst, C, HW, src_img_stride);
