@@ -116,7 +116,7 @@ __device__ __forceinline__ float4 accumulate_range(const StagePoint *__restrict_
 // i.e. C4 / 2 warps, and every warp combines / writes two 128-bit channel quads of all 32 cells.
 template <typename FeatT, int kC4>
 #ifndef RCB_FWD_MINCTAS
-#define RCB_FWD_MINCTAS 3
+#define RCB_FWD_MINCTAS 4  // measured: 3 -> 104 us, 4 -> 99 us, 5+ -> no gain (the row loads need the registers)
 #endif
 #ifndef RCB_FWD_UNROLL
 #define RCB_FWD_UNROLL 8
