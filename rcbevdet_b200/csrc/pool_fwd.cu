@@ -80,9 +80,19 @@ __device__ __forceinline__ void fma_row(float4 &acc, const float4 v, const float
   acc = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
-#ifdef RCB_PROFILE_PHASES
-__device__ long long g_fwd_prof[8192 * 8];
-#define RCB_T(k) if (threadIdx.x == 0 && blockIdx.x < 8192) g_fwd_prof[blockIdx.x * 8 + (k)] = clock64();
+#ifdef RCB_PROFILE_PHASES  // debug build only: per-CTA phase stamps read by tools/prof_fwd_phases.py
+__device__ long long g_fwd_prof[16384 * 8];
+__device__ __forceinline__ long long rcb_gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int rcb_smid() {
+  int v;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+  return v;
+}
+#define RCB_T(k) if (threadIdx.x == 0 && blockIdx.x < 16384) g_fwd_prof[blockIdx.x * 8 + (k)] = rcb_gtime();
 #else
 #define RCB_T(k)
 #endif
@@ -181,7 +191,7 @@ __global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ?
   RCB_T(1)
   const int total = seg_off[kTileY];
 #ifdef RCB_PROFILE_PHASES
-  if (threadIdx.x == 0 && blockIdx.x < 8192) g_fwd_prof[blockIdx.x * 8 + 7] = total;
+  if (threadIdx.x == 0 && blockIdx.x < 16384) g_fwd_prof[blockIdx.x * 8 + 7] = total, g_fwd_prof[blockIdx.x * 8 + 6] = rcb_smid();
 #endif
 
   const int group = tid / C4, q = tid - group * C4;
@@ -285,6 +295,7 @@ __global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ?
       st_stream_f32(d4 + 3 * (size_t)p.cells_per_sample, racc[k].w);
     }
   }
+  RCB_T(5)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -436,5 +447,10 @@ extern "C" int rcb_bev_pool_v2_fwd(const rcb_pool_desc *d, const float *depth, c
 #ifdef RCB_PROFILE_PHASES
 extern "C" int rcb_debug_fwd_prof(long long *host, int n) {
   return (int)cudaMemcpyFromSymbol(host, rcb::g_fwd_prof, sizeof(long long) * n);
+}
+extern "C" int rcb_debug_fwd_prof_reset() {
+  void *p = nullptr;
+  cudaGetSymbolAddress(&p, rcb::g_fwd_prof);
+  return (int)cudaMemset(p, 0, sizeof(long long) * 16384 * 8);
 }
 #endif
