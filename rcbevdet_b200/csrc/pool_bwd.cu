@@ -215,11 +215,42 @@ __global__ void __launch_bounds__(256, 3) k_pool_bwd_pixels16(BwdPixelParams p) 
         my_cell = __ldg(p.point_cell + col + my_d * p.HW);
         my_w = __ldg(p.depth + col + my_d * p.HW);
       }
-      float dot[16];
+      // Consecutive depth bins of a pixel often fall into the same BEV cell (1.42 bins per (cell,
+      // pixel) pair on average: a ray crosses a 0.8 m cell in ~1.6 steps of 0.5 m).  Such a run
+      // shares its out_grad row and its dot product, so only the run's first bin (at most 4 bins per
+      // group) loads the row: it carries the group's summed depth weight for feat_grad and hands
+      // its dot product to the followers afterwards.  depth_grad is bit-identical to the unmerged
+      // computation; feat_grad differs by the rounding of (w1 + w2) * g vs w1 * g + w2 * g.
+      const int prev_cell = __shfl_up_sync(kFull, my_cell, 1, 16);
+      const bool starts_run = l16 == 0 || my_cell != prev_cell;
+      const unsigned starts16 = (__ballot_sync(kFull, starts_run) >> (half * 16)) & 0xffffu;
+      const int run_head = 31 - __clz((int)(starts16 & ((2u << l16) - 1u)));  // lane where my run starts
+      const int pos = (l16 - run_head) & 3;                                   // position inside a group of <= 4
+      const bool is_head = my_cell >= 0 && pos == 0;
+      const int head_lane = l16 - pos;
+      float w_group = my_w;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const int cell = __shfl_sync(kFull, my_cell, k, 16);
-        const float w = __shfl_sync(kFull, my_w, k, 16);
+      for (int j = 1; j < 4; ++j) {
+        const float wn = __shfl_down_sync(kFull, my_w, j, 16);
+        const int pn = __shfl_down_sync(kFull, pos, j, 16);
+        if (l16 + j < 16 && pn == j) w_group += wn;  // lane + j is the j-th follower of my group
+      }
+      // The heads are compacted: slot j of a half-warp is its j-th head.  Every slot's body is
+      // issued (predicated) whether or not it is used, so fewer slots = fewer issue cycles: the
+      // first kHeadSlots slots run unconditionally (their row loads are hoisted together by the
+      // compiler), the rest only when some half has that many heads.
+      const unsigned heads16 = (__ballot_sync(kFull, is_head) >> (half * 16)) & 0xffffu;
+      const int n_heads = __popc(heads16);
+      const int n_heads_max = max(n_heads, __shfl_xor_sync(kFull, n_heads, 16));
+      // lane l16 (as slot index) looks up which lane holds head number l16
+      const int src_lane = l16 < n_heads ? (int)__fns(heads16, 0, l16 + 1) : 0;
+      const int slot_cell = __shfl_sync(kFull, my_cell, src_lane, 16);
+      const float slot_w = __shfl_sync(kFull, w_group, src_lane, 16);
+      const int my_slot_cell = l16 < n_heads ? slot_cell : -1;
+      float dot[16];
+      auto slot_body = [&](int k) {
+        const int cell = __shfl_sync(kFull, my_slot_cell, k, 16);
+        const float w = __shfl_sync(kFull, slot_w, k, 16);
         float s = 0.f;
         if (cell >= 0) {
           const unsigned row_off = (unsigned)cell * (unsigned)(kC * 4);
@@ -245,10 +276,24 @@ __global__ void __launch_bounds__(256, 3) k_pool_bwd_pixels16(BwdPixelParams p) 
             gs[j] = fmaf(g, w, gs[j]);
           }
         }
-        dot[k] = s;
+        return s;
+      };
+#ifndef RCB_BWD_HEAD_SLOTS
+#define RCB_BWD_HEAD_SLOTS 10
+#endif
+      constexpr int kHeadSlots = RCB_BWD_HEAD_SLOTS;
+#pragma unroll
+      for (int k = 0; k < kHeadSlots; ++k) dot[k] = slot_body(k);
+#pragma unroll
+      for (int k = kHeadSlots; k < 16; ++k) dot[k] = 0.f;
+      if (n_heads_max > kHeadSlots) {
+#pragma unroll
+        for (int k = kHeadSlots; k < 16; ++k) dot[k] = slot_body(k);
       }
-      const float total = transpose_reduce16(dot, l16);
-      if (live && my_d < p.D) p.depth_grad[col + my_d * p.HW] = total;
+      float total = transpose_reduce16(dot, l16);
+      // a bin's value sits in the slot of its group head: slot = rank of the head lane among the heads
+      total = __shfl_sync(kFull, total, __popc(heads16 & ((1u << head_lane) - 1u)), 16);
+      if (live && my_d < p.D) p.depth_grad[col + my_d * p.HW] = my_cell >= 0 ? total : 0.f;
     }
     if (live) {
       float *grow = p.feat_grad + (size_t)pix * kC;
