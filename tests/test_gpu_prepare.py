@@ -96,6 +96,34 @@ def test_long_cells_every_sort_tier(n_cells_hit, P):
     assert got[3].numel() == len(np.unique(which))
 
 
+@pytest.mark.parametrize("grid,B,P,hot", [
+    ((64, 32, 1), 1, 30000, 0.0),       # 2^11 cells: buckets of two cells
+    ((64, 64, 1), 1, 50000, 0.5),       # exactly 2^12 cells, half the points in one BEV row -> multi-chunk buckets
+    ((100, 50, 3), 2, 120000, 0.3),     # 30000 cells, not a power of two, Z > 1
+    ((128, 128, 1), 3, 200000, 0.7),    # R50 grid, 140k points in one row of one sample
+    ((1024, 1024, 1), 1, 150000, 0.2),  # 2^20 cells: 1024-cell buckets
+    ((1500, 1000, 1), 1, 100000, 0.2),  # > 2^20 cells: three plain LSD passes
+])
+def test_two_level_sort_grids(grid, B, P, hot):
+    """Every sort path of the prepare stage (one LSD pass, global pass + bucket sort with one
+    and several chunks per bucket, three LSD passes), bit-exact against the oracle."""
+    rng = np.random.default_rng(P + grid[0])
+    gx, gy, gz = grid
+    per = P // B
+    coor = np.empty((B, 1, per, 1, 1, 3), np.float32)
+    coor[..., 0] = rng.random((B, 1, per, 1, 1), dtype=np.float32) * (gx + 4) - 2
+    coor[..., 1] = rng.random((B, 1, per, 1, 1), dtype=np.float32) * (gy + 4) - 2
+    coor[..., 2] = rng.random((B, 1, per, 1, 1), dtype=np.float32) * (gz + 1) - 0.5
+    n_hot = int(per * hot)
+    if n_hot:  # concentrate points of the last sample in one BEV row (and a few cells of it)
+        coor[B - 1, 0, :n_hot, 0, 0, 1] = gy // 2 + 0.5
+        coor[B - 1, 0, : n_hot // 2, 0, 0, 0] = rng.integers(0, 3, size=n_hot // 2) + 0.5
+    lo = np.float32([0.0, 0.0, 0.0])
+    iv = np.float32([1.0, 1.0, 1.0])
+    sz = np.float32([gx, gy, gz])
+    _check_against_oracle(coor, lo, iv, sz)
+
+
 def test_truncation_toward_zero_and_boundaries():
     """view_transformer.py:232 `.long()`: voxel coordinates in (-1, 0) are KEPT in cell 0; exactly
     -1.0 and exactly `size` are dropped."""
