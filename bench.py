@@ -39,6 +39,10 @@ WORKLOAD = dict(workload="RCBEVDet R50 256x704 LSS view transform: prepare + bev
                          "B=8/GPU, 6 cams, D=118, 16x44 features, C=80 -> 128x128 BEV (BASELINE config 2)",
                 batch_per_gpu=8, cams=6, D=118, H=16, W=44, C=80, bev=[1, 128, 128])
 N_SETS = 3  # rotating input sets
+# Per-stage CUDA events are recorded on every 8th timed step: ten event records
+# between the kernels cost ~18 us per step (measured: 375.6 vs 357.7 us), so instrumenting every
+# step would tax the number the stages are meant to explain.  All steps do identical work.
+STAGE_EVENT_EVERY = 8
 
 
 def _peaks():
@@ -159,7 +163,7 @@ def run_ours(args):
     stream = torch.cuda.current_stream(dev)
 
     stage_names = ("prepare", "feat_rows", "fwd", "og_rows", "bwd")
-    n_kernels = {"prepare": 8, "feat_rows": 1, "fwd": 1, "og_rows": 1, "bwd": 1}
+    n_kernels = {"prepare": 5, "feat_rows": 1, "fwd": 1, "og_rows": 1, "bwd": 1}
     stage_events = {s: [] for s in stage_names}
 
     def step(i, record):
@@ -224,14 +228,17 @@ def run_ours(args):
     clocks.start()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
+    event_phase = min(STAGE_EVENT_EVERY // 2, args.steps - 1)  # not step 0: the launch queue is still empty there
     t0.record(stream)
+    host_t0 = time.perf_counter()
     for i in range(args.steps):
-        step(i, True)
+        step(i, i % STAGE_EVENT_EVERY == event_phase)
     t1.record(stream)
+    host_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps   # launch-side time per step
     barrier()
     clk = clocks.stop()
     total_ms = t0.elapsed_time(t1)
-    stage_ms = {s: sum(a.elapsed_time(b) for a, b in stage_events[s]) / args.steps for s in stage_names}
+    stage_ms = {s: sum(a.elapsed_time(b) for a, b in stage_events[s]) / len(stage_events[s]) for s in stage_names}
 
     # ---- optional variant, reported beside the fp32 numbers (not part of `value`): bf16 context rows,
     #      fp32 accumulation (north_star: bf16 context within 1e-2) ------------------------------
@@ -366,6 +373,8 @@ def run_ours(args):
                     "api": "rcbevdet_b200.voxel_pooling_v2 + autograd backward; pinned host in/out, 3 streams x 2 slots (upload / kernels / download overlapped)", "checksum": e2e_check},
             "gpu_launches": args.steps * sum(n_kernels.values()),
             "stages_ms": {s: round(v, 5) for s, v in stage_ms.items()},
+            "host_launch_ms_per_step": round(host_ms, 5),
+            "stage_events": f"every {STAGE_EVENT_EVERY}th timed step ({len(stage_events['fwd'])} of {args.steps})",
             "stage_frac_of_hbm_peak": {s: round(alg[s] / (stage_ms[s] * 1e-3) / 1e9 / peak, 4)
                                        for s in ("prepare", "fwd", "bwd")},
             "stage_algorithmic_bytes": alg,

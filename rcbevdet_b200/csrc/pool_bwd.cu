@@ -136,21 +136,39 @@ __global__ void __launch_bounds__(256) k_pool_bwd_pixels(BwdPixelParams p) {
 // Half-warp variant (C a multiple of 16): 16 lanes per pixel, two adjacent pixels per warp, each
 // lane owning kNQ 128-bit quads (channels 64*j + 4*l .. +3) and kNS scalars (channels
 // 64*kNQ + 16*s + l).  C = 80 -> one quad + one scalar per lane: no idle lanes (the 32-lane
-// kernel above runs 20 of 32), half the shuffles per point, and the 16-way transposed
-// reduction costs 15 shuffles per 16 depth bins.
+// kernel above runs 20 of 32).
+//
+// The kernel is bound by the L1 data pipe (ncu: 71 % of its wavefronts, shuffles included), so
+// everything that is not an out_grad row goes through it as cheaply as possible:
+//  * a CTA owns 16 consecutive pixels; their point_cell / depth columns (stride HW words per
+//    depth bin) are fetched as 64-byte runs across the 16 pixels into shared memory and read back
+//    column-wise, depth_grad leaves the same way: 2 wavefronts per 32 words instead of ~20;
+//  * the compacted (cell, weight) slots of a half-warp are exchanged through 144 bytes of shared
+//    memory, two slots per 128-bit load, instead of two shuffles per slot;
+//  * the per-bin dot products are reduced with a transposed butterfly sized to the number of
+//    slots in use (8 shuffles for <= 8 slots, 15 otherwise).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float transpose_reduce16(float (&v)[16], int l16) {
+template <int kSlots>
+__device__ __forceinline__ float transpose_reduce16(float (&v)[kSlots], int l16) {
+  static_assert(kSlots == 8 || kSlots == 16, "slot tiers");
 #pragma unroll
   for (int h = 8; h >= 1; h >>= 1) {
+    constexpr int kTop = kSlots;
+    const int n = (kTop * h) / 16;  // values still held per lane after this step
+    if (n == 0) {  // kSlots == 8, h == 1: both lanes of a pair hold the same slot
+      v[0] += __shfl_xor_sync(kFull, v[0], 1);
+      break;
+    }
 #pragma unroll
-    for (int k = 0; k < h; ++k) {
+    for (int k = 0; k < kSlots / 2; ++k) {
+      if (k >= n) break;
       const bool up = l16 & h;
-      const float send = up ? v[k] : v[k + h];
-      const float keep = up ? v[k + h] : v[k];
+      const float send = up ? v[k] : v[k + n];
+      const float keep = up ? v[k + n] : v[k];
       v[k] = keep + __shfl_xor_sync(kFull, send, h);
     }
   }
-  return v[0];  // lane l16 holds the total of index l16
+  return v[0];  // kSlots == 16: lane l holds slot l; kSlots == 8: lanes 2s and 2s + 1 hold slot s
 }
 
 template <typename T>
@@ -172,23 +190,31 @@ struct Elem<__half> {
   }
 };
 
+constexpr int kBwdTilePitch = 17;        // words per depth bin in the staged tiles (16 pixels + 1)
+constexpr int kBwdSlotPitch = 18;        // int2 per half-warp slot table (16 slots + 16 bytes)
+constexpr int kBwdMaxChunk = 128;        // depth bins staged at once
+__host__ __device__ inline size_t bwd16_smem_bytes(int d_chunk) {
+  return (size_t)3 * d_chunk * kBwdTilePitch * 4 + (size_t)8 * 2 * kBwdSlotPitch * 8;
+}
+
 template <typename FeatT, int kNQ, int kNS>
-__global__ void __launch_bounds__(256, 3) k_pool_bwd_pixels16(BwdPixelParams p) {
+__global__ void __launch_bounds__(256, 4) k_pool_bwd_pixels16(BwdPixelParams p, int d_chunk) {
   constexpr int kC = 64 * kNQ + 16 * kNS;
-  const int lane = lane_id(), l16 = lane & 15, half = lane >> 4;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
+  extern __shared__ __align__(16) unsigned char bwd_smem[];
+  int *s_cell = reinterpret_cast<int *>(bwd_smem);            // [d_chunk][17]
+  float *s_w = reinterpret_cast<float *>(s_cell + d_chunk * kBwdTilePitch);
+  float *s_dg = s_w + d_chunk * kBwdTilePitch;
+  int2 *s_slot = reinterpret_cast<int2 *>(s_dg + d_chunk * kBwdTilePitch);  // [8 warps][2 halves][18]
+  const int lane = lane_id(), l16 = lane & 15, half = lane >> 4, warp = threadIdx.x >> 5;
+  int2 *my_slots = s_slot + (warp * 2 + half) * kBwdSlotPitch;
   const char *og = reinterpret_cast<const char *>(p.out_grad_rows);
   const char *feat = static_cast<const char *>(p.feat);
-  for (int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pair * 2 < p.n_pixels; pair += warps) {
-    // The two halves of a warp hold horizontally adjacent pixels: their depth / point_cell /
-    // depth_grad words share 32-byte sectors.  (Walking pixel columns instead would let both halves
-    // hit the same out_grad rows, but measured 20 % slower: those strided 4-byte accesses then
-    // waste 7/8 of every sector.)
-    const int pix = pair * 2 + half;
+  const int px_mine = warp * 2 + half;  // my pixel inside the CTA's group of 16
+  const int px_load = threadIdx.x & 15;  // the pixel column this thread stages
+  for (int group = blockIdx.x; group * 16 < p.n_pixels; group += gridDim.x) {
+    const int pix = group * 16 + px_mine;
     const bool live = pix < p.n_pixels;
     const int pix_c = live ? pix : p.n_pixels - 1;
-    const int bn = pix_c / p.HW, hw = pix_c - bn * p.HW;
-    const int col = bn * p.DHW + hw;  // point index of depth bin 0
     float4 fq[kNQ > 0 ? kNQ : 1], gq[kNQ > 0 ? kNQ : 1];
     float fs[kNS > 0 ? kNS : 1], gs[kNS > 0 ? kNS : 1];
     const char *frow = feat + (size_t)pix_c * kC * sizeof(FeatT);
@@ -202,98 +228,128 @@ __global__ void __launch_bounds__(256, 3) k_pool_bwd_pixels16(BwdPixelParams p) 
       fs[j] = Elem<FeatT>::load(frow + (64 * kNQ + 16 * j + l16) * sizeof(FeatT));
       gs[j] = 0.f;
     }
+    // staging role: this thread moves depth bins (threadIdx.x >> 4) + 16 k of pixel column px_load
+    const int pix_l = group * 16 + px_load;
+    const bool live_l = pix_l < p.n_pixels;
+    const int bn_l = (live_l ? pix_l : 0) / p.HW;
+    const int col_l = bn_l * p.DHW + ((live_l ? pix_l : 0) - bn_l * p.HW);  // point index of depth bin 0
     // per-lane bases of the quad part and of the scalar tail of an out_grad row, pinned in
     // registers so that each row address is ONE 32x32+64 multiply-add of the cell index
     const char *og_lane = og + (size_t)l16 * 16;
     const char *og_tail = og + 256 * kNQ + (size_t)l16 * 4;
     asm volatile("" : "+l"(og_lane), "+l"(og_tail));
-    for (int d0 = 0; d0 < p.D; d0 += 16) {
-      const int my_d = d0 + l16;
-      int my_cell = -1;
-      float my_w = 0.f;
-      if (live && my_d < p.D) {
-        my_cell = __ldg(p.point_cell + col + my_d * p.HW);
-        my_w = __ldg(p.depth + col + my_d * p.HW);
-      }
-      // Consecutive depth bins of a pixel often fall into the same BEV cell (1.42 bins per (cell,
-      // pixel) pair on average: a ray crosses a 0.8 m cell in ~1.6 steps of 0.5 m).  Such a run
-      // shares its out_grad row and its dot product, so only the run's first bin (at most 4 bins per
-      // group) loads the row: it carries the group's summed depth weight for feat_grad and hands
-      // its dot product to the followers afterwards.  depth_grad is bit-identical to the unmerged
-      // computation; feat_grad differs by the rounding of (w1 + w2) * g vs w1 * g + w2 * g.
-      const int prev_cell = __shfl_up_sync(kFull, my_cell, 1, 16);
-      const bool starts_run = l16 == 0 || my_cell != prev_cell;
-      const unsigned starts16 = (__ballot_sync(kFull, starts_run) >> (half * 16)) & 0xffffu;
-      const int run_head = 31 - __clz((int)(starts16 & ((2u << l16) - 1u)));  // lane where my run starts
-      const int pos = (l16 - run_head) & 3;                                   // position inside a group of <= 4
-      const bool is_head = my_cell >= 0 && pos == 0;
-      const int head_lane = l16 - pos;
-      float w_group = my_w;
-#pragma unroll
-      for (int j = 1; j < 4; ++j) {
-        const float wn = __shfl_down_sync(kFull, my_w, j, 16);
-        const int pn = __shfl_down_sync(kFull, pos, j, 16);
-        if (l16 + j < 16 && pn == j) w_group += wn;  // lane + j is the j-th follower of my group
-      }
-      // The heads are compacted: slot j of a half-warp is its j-th head.  Every slot's body is
-      // issued (predicated) whether or not it is used, so fewer slots = fewer issue cycles: the
-      // first kHeadSlots slots run unconditionally (their row loads are hoisted together by the
-      // compiler), the rest only when some half has that many heads.
-      const unsigned heads16 = (__ballot_sync(kFull, is_head) >> (half * 16)) & 0xffffu;
-      const int n_heads = __popc(heads16);
-      const int n_heads_max = max(n_heads, __shfl_xor_sync(kFull, n_heads, 16));
-      // lane l16 (as slot index) looks up which lane holds head number l16
-      const int src_lane = l16 < n_heads ? (int)__fns(heads16, 0, l16 + 1) : 0;
-      const int slot_cell = __shfl_sync(kFull, my_cell, src_lane, 16);
-      const float slot_w = __shfl_sync(kFull, w_group, src_lane, 16);
-      const int my_slot_cell = l16 < n_heads ? slot_cell : -1;
-      float dot[16];
-      auto slot_body = [&](int k) {
-        const int cell = __shfl_sync(kFull, my_slot_cell, k, 16);
-        const float w = __shfl_sync(kFull, slot_w, k, 16);
-        float s = 0.f;
-        if (cell >= 0) {
-          const unsigned row_off = (unsigned)cell * (unsigned)(kC * 4);
-          const char *row = og_lane + row_off;
-          const float2 ww = make_float2(w, w);
-          float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int j = 0; j < kNQ; ++j) {
-            const float4 g = __ldg(reinterpret_cast<const float4 *>(row + 256 * j));
-            const float2 glo = make_float2(g.x, g.y), ghi = make_float2(g.z, g.w);
-            acc = __ffma2_rn(glo, make_float2(fq[j].x, fq[j].y), acc);
-            acc = __ffma2_rn(ghi, make_float2(fq[j].z, fq[j].w), acc);
-            const float2 a = __ffma2_rn(glo, ww, make_float2(gq[j].x, gq[j].y));
-            const float2 b = __ffma2_rn(ghi, ww, make_float2(gq[j].z, gq[j].w));
-            gq[j] = make_float4(a.x, a.y, b.x, b.y);
-          }
-          s = acc.x + acc.y;
-#pragma unroll
-          for (int j = 0; j < kNS; ++j) {
-            // scalar tail: channel 64*kNQ + 16*j + l16
-            const float g = __ldg(reinterpret_cast<const float *>(og_tail + row_off + 64 * j));
-            s = fmaf(g, fs[j], s);
-            gs[j] = fmaf(g, w, gs[j]);
-          }
+
+    for (int dc0 = 0; dc0 < p.D; dc0 += d_chunk) {
+      const int n_d = min(d_chunk, p.D - dc0);
+      for (int d = threadIdx.x >> 4; d < d_chunk; d += 16) {
+        int c = -1;
+        float w = 0.f;
+        if (live_l && d < n_d) {
+          c = __ldg(p.point_cell + col_l + (dc0 + d) * p.HW);
+          w = __ldg(p.depth + col_l + (dc0 + d) * p.HW);
         }
-        return s;
-      };
-#ifndef RCB_BWD_HEAD_SLOTS
-#define RCB_BWD_HEAD_SLOTS 10
-#endif
-      constexpr int kHeadSlots = RCB_BWD_HEAD_SLOTS;
-#pragma unroll
-      for (int k = 0; k < kHeadSlots; ++k) dot[k] = slot_body(k);
-#pragma unroll
-      for (int k = kHeadSlots; k < 16; ++k) dot[k] = 0.f;
-      if (n_heads_max > kHeadSlots) {
-#pragma unroll
-        for (int k = kHeadSlots; k < 16; ++k) dot[k] = slot_body(k);
+        s_cell[d * kBwdTilePitch + px_load] = c;
+        s_w[d * kBwdTilePitch + px_load] = w;
       }
-      float total = transpose_reduce16(dot, l16);
-      // a bin's value sits in the slot of its group head: slot = rank of the head lane among the heads
-      total = __shfl_sync(kFull, total, __popc(heads16 & ((1u << head_lane) - 1u)), 16);
-      if (live && my_d < p.D) p.depth_grad[col + my_d * p.HW] = my_cell >= 0 ? total : 0.f;
+      __syncthreads();
+
+      for (int d0 = 0; d0 < n_d; d0 += 16) {
+        const int my_cell = s_cell[(d0 + l16) * kBwdTilePitch + px_mine];
+        const float my_w = s_w[(d0 + l16) * kBwdTilePitch + px_mine];
+        // Consecutive depth bins of a pixel often fall into the same BEV cell (1.42 bins per (cell,
+        // pixel) pair on average: a ray crosses a 0.8 m cell in ~1.6 steps of 0.5 m).  Such a run
+        // shares its out_grad row and its dot product, so only the run's first bin (at most 4 bins
+        // per group) loads the row: it carries the group's summed depth weight for feat_grad and
+        // hands its dot product to the followers afterwards.  depth_grad is bit-identical to the
+        // unmerged computation; feat_grad differs by the rounding of (w1 + w2) * g vs w1 * g + w2 * g.
+        const int prev_cell = __shfl_up_sync(kFull, my_cell, 1, 16);
+        const bool starts_run = l16 == 0 || my_cell != prev_cell;
+        const unsigned starts16 = (__ballot_sync(kFull, starts_run) >> (half * 16)) & 0xffffu;
+        const int run_head = 31 - __clz((int)(starts16 & ((2u << l16) - 1u)));  // lane where my run starts
+        const int pos = (l16 - run_head) & 3;                                   // position inside a group of <= 4
+        const bool is_head = my_cell >= 0 && pos == 0;
+        const int head_lane = l16 - pos;
+        float w_group = my_w;
+#pragma unroll
+        for (int j = 1; j < 4; ++j) {
+          const float wn = __shfl_down_sync(kFull, my_w, j, 16);
+          const int pn = __shfl_down_sync(kFull, pos, j, 16);
+          if (l16 + j < 16 && pn == j) w_group += wn;  // lane + j is the j-th follower of my group
+        }
+        // The heads are compacted: slot j of a half-warp is its j-th head, published through the
+        // half-warp's slot table (unused slots read as cell -1).
+        const unsigned heads16 = (__ballot_sync(kFull, is_head) >> (half * 16)) & 0xffffu;
+        const int n_heads = __popc(heads16);
+        const int n_heads_max = max(n_heads, __shfl_xor_sync(kFull, n_heads, 16));
+        __syncwarp();  // the previous batch's slot reads are done
+        if (is_head) my_slots[__popc(heads16 & ((1u << l16) - 1u))] = make_int2(my_cell, __float_as_int(w_group));
+        if (l16 >= n_heads) my_slots[l16] = make_int2(-1, 0);
+        __syncwarp();
+
+        auto slot_pair = [&](int k2, float &dot_a, float &dot_b) {  // slots 2*k2 and 2*k2 + 1
+          const int4 sl = *reinterpret_cast<const int4 *>(my_slots + 2 * k2);
+          const int cells[2] = {sl.x, sl.z};
+          const float ws[2] = {__int_as_float(sl.y), __int_as_float(sl.w)};
+          float dots[2];
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            float s = 0.f;
+            if (cells[t] >= 0) {
+              const unsigned row_off = (unsigned)cells[t] * (unsigned)(kC * 4);
+              const char *row = og_lane + row_off;
+              const float2 ww = make_float2(ws[t], ws[t]);
+              float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int j = 0; j < kNQ; ++j) {
+                const float4 g = __ldg(reinterpret_cast<const float4 *>(row + 256 * j));
+                const float2 glo = make_float2(g.x, g.y), ghi = make_float2(g.z, g.w);
+                acc = __ffma2_rn(glo, make_float2(fq[j].x, fq[j].y), acc);
+                acc = __ffma2_rn(ghi, make_float2(fq[j].z, fq[j].w), acc);
+                const float2 a = __ffma2_rn(glo, ww, make_float2(gq[j].x, gq[j].y));
+                const float2 b = __ffma2_rn(ghi, ww, make_float2(gq[j].z, gq[j].w));
+                gq[j] = make_float4(a.x, a.y, b.x, b.y);
+              }
+              s = acc.x + acc.y;
+#pragma unroll
+              for (int j = 0; j < kNS; ++j) {
+                // scalar tail: channel 64*kNQ + 16*j + l16
+                const float g = __ldg(reinterpret_cast<const float *>(og_tail + row_off + 64 * j));
+                s = fmaf(g, fs[j], s);
+                gs[j] = fmaf(g, ws[t], gs[j]);
+              }
+            }
+            dots[t] = s;
+          }
+          dot_a = dots[0], dot_b = dots[1];
+        };
+        // a bin's value sits in the slot of its group head: slot = rank of the head lane among the heads
+        const int my_slot = __popc(heads16 & ((1u << head_lane) - 1u));
+        float total;
+        if (n_heads_max <= 8) {  // warp-uniform
+          float dot[8];
+#pragma unroll
+          for (int k2 = 0; k2 < 4; ++k2) slot_pair(k2, dot[2 * k2], dot[2 * k2 + 1]);
+          total = transpose_reduce16<8>(dot, l16);
+          total = __shfl_sync(kFull, total, 2 * my_slot, 16);
+        } else {
+          float dot[16];
+#pragma unroll
+          for (int k2 = 0; k2 < 6; ++k2) slot_pair(k2, dot[2 * k2], dot[2 * k2 + 1]);
+#pragma unroll
+          for (int k = 12; k < 16; ++k) dot[k] = 0.f;
+          if (n_heads_max > 12) {
+#pragma unroll
+            for (int k2 = 6; k2 < 8; ++k2) slot_pair(k2, dot[2 * k2], dot[2 * k2 + 1]);
+          }
+          total = transpose_reduce16<16>(dot, l16);
+          total = __shfl_sync(kFull, total, my_slot, 16);
+        }
+        s_dg[(d0 + l16) * kBwdTilePitch + px_mine] = my_cell >= 0 ? total : 0.f;
+      }
+      __syncthreads();
+      for (int d = threadIdx.x >> 4; d < n_d; d += 16)
+        if (live_l) p.depth_grad[col_l + (dc0 + d) * p.HW] = s_dg[d * kBwdTilePitch + px_load];
+      // (the next chunk's staging writes s_cell / s_w only; s_dg is rewritten after its barrier)
     }
     if (live) {
       float *grow = p.feat_grad + (size_t)pix * kC;
@@ -338,9 +394,11 @@ static int launch_pixels(BwdPixelParams &p, int sms, cudaStream_t s) {
   const int C = p.C4 * 4;
   const int grid16 = max(1, min(ceil_div(p.n_pixels, 16), sms * 24));
   if (C == 80 || C == 64 || C == 128) {
-    if (C == 80) k_pool_bwd_pixels16<FeatT, 1, 1><<<grid16, 256, 0, s>>>(p);
-    else if (C == 64) k_pool_bwd_pixels16<FeatT, 1, 0><<<grid16, 256, 0, s>>>(p);
-    else k_pool_bwd_pixels16<FeatT, 2, 0><<<grid16, 256, 0, s>>>(p);
+    const int d_chunk = min(kBwdMaxChunk, ceil_div(p.D, 16) * 16);
+    const size_t smem = bwd16_smem_bytes(d_chunk);  // <= 28 KB
+    if (C == 80) k_pool_bwd_pixels16<FeatT, 1, 1><<<grid16, 256, smem, s>>>(p, d_chunk);
+    else if (C == 64) k_pool_bwd_pixels16<FeatT, 1, 0><<<grid16, 256, smem, s>>>(p, d_chunk);
+    else k_pool_bwd_pixels16<FeatT, 2, 0><<<grid16, 256, smem, s>>>(p, d_chunk);
     RCB_LAUNCH_CHECK();
     return RCB_OK;
   }

@@ -48,6 +48,7 @@ struct FwdTileParams {
   int cells_per_sample;
   int layout;
   int B;
+  FastDiv by_B, by_tiles_x;  // block index -> (sample, patch column, patch row) without IDIV
 };
 
 struct __align__(8) StagePoint {
@@ -154,11 +155,11 @@ __global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ?
   // Launch order: patches nearest the grid centre first, samples interleaved.  Point density
   // peaks around the ego vehicle (a patch there holds ~8x the average), so the long patches start
   // at once instead of forming the kernel's tail.  Any order is correct; this one is a heuristic.
-  int t = blockIdx.x;
-  const int b = t % p.B;
-  t /= p.B;
-  const int tx_i = zigzag_from_centre(t % p.tiles_x, p.tiles_x);
-  const int tr_i = zigzag_from_centre(t / p.tiles_x, p.tiles_r);
+  const int t = (int)p.by_B.div(blockIdx.x);
+  const int b = (int)blockIdx.x - t * p.B;
+  const int t_r = (int)p.by_tiles_x.div((unsigned)t);
+  const int tx_i = zigzag_from_centre(t - t_r * p.tiles_x, p.tiles_x);
+  const int tr_i = zigzag_from_centre(t_r, p.tiles_r);
   const int x0 = tx_i * kTileX, r0 = tr_i * kTileY;
   const int nx = min(kTileX, p.X - x0), nr = min(kTileY, p.R - r0);
   const int cell_base = b * p.cells_per_sample;
@@ -418,6 +419,7 @@ extern "C" int rcb_bev_pool_v2_fwd(const rcb_pool_desc *d, const float *depth, c
     p.X = d->X, p.R = d->Z * d->Y;
     p.tiles_x = ceil_div(p.X, kTileX), p.tiles_r = ceil_div(p.R, kTileY);
     p.cells_per_sample = cps, p.layout = d->layout, p.B = d->B;
+    p.by_B = FastDiv::make((unsigned)p.B), p.by_tiles_x = FastDiv::make((unsigned)p.tiles_x);
     switch (d->feat_dtype) {
       case RCB_DTYPE_F32: return launch_tile<float>(d, p, s);
       case RCB_DTYPE_BF16: return launch_tile<__nv_bfloat16>(d, p, s);
