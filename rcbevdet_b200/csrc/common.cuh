@@ -21,6 +21,28 @@
 
 namespace rcb {
 
+// Programmatic dependent launch: a kernel launched with launch_pdl() may be scheduled while the
+// previous kernel of the stream is still draining; pdl_prologue() -- the first statement of every
+// such kernel -- blocks until that kernel has completed and its writes are visible, then lets the
+// next launch do the same.  It hides launch latency and the ramp-up of each grid, nothing else;
+// under a normal launch both instructions are no-ops.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args &&...args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 

@@ -24,6 +24,7 @@ __device__ __forceinline__ unsigned short convert_elem<float, unsigned short>(fl
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256) k_planes_to_rows(const TIn *__restrict__ src, TOut *__restrict__ dst,
                                                         int C, int HW, long long src_img_stride) {
+  pdl_prologue();
   __shared__ TOut tile[32][33];
   const int img = blockIdx.z;
   const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(256) k_planes_to_rows(const TIn *__restrict__ 
 constexpr int kV4Pixels = 64;
 __global__ void __launch_bounds__(256) k_planes_to_rows_v4(const float *__restrict__ src, float *__restrict__ dst,
                                                            int C, int HW, long long src_img_stride) {
+  pdl_prologue();
   extern __shared__ float tile_v4[];  // [kV4Pixels][C + 1]
   const int P = C + 1;
   const int img = blockIdx.y;
@@ -84,13 +86,12 @@ int planes_to_rows_launch(const void *src, void *dst, int n_img, int C, int HW,
     if (smem > 48 * 1024)
       RCB_CUDA_TRY(cudaFuncSetAttribute(k_planes_to_rows_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 g4(ceil_div(HW, kV4Pixels), n_img);
-    k_planes_to_rows_v4<<<g4, 256, smem, s>>>((const float *)src, (float *)dst, C, HW, src_img_stride);
-    RCB_LAUNCH_CHECK();
+    RCB_CUDA_TRY(launch_pdl(k_planes_to_rows_v4, g4, 256, smem, s, (const float *)src, (float *)dst, C, HW, src_img_stride));
     return RCB_OK;
   }
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), n_img);
   if (elem_bytes == 4)
-    k_planes_to_rows<float, float><<<grid, 256, 0, s>>>((const float *)src, (float *)dst, C, HW, src_img_stride);
+    RCB_CUDA_TRY(launch_pdl(k_planes_to_rows<float, float>, grid, 256, 0, s, (const float *)src, (float *)dst, C, HW, src_img_stride));
   else if (elem_bytes == 2)
     k_planes_to_rows<unsigned short, unsigned short>
         <<<grid, 256, 0, s>>>((const unsigned short *)src, (unsigned short *)dst, C, HW, src_img_stride);

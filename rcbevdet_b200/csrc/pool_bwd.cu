@@ -199,6 +199,7 @@ __host__ __device__ inline size_t bwd16_smem_bytes(int d_chunk) {
 
 template <typename FeatT, int kNQ, int kNS>
 __global__ void __launch_bounds__(256, 4) k_pool_bwd_pixels16(BwdPixelParams p, int d_chunk) {
+  pdl_prologue();
   constexpr int kC = 64 * kNQ + 16 * kNS;
   extern __shared__ __align__(16) unsigned char bwd_smem[];
   int *s_cell = reinterpret_cast<int *>(bwd_smem);            // [d_chunk][17]
@@ -396,10 +397,9 @@ static int launch_pixels(BwdPixelParams &p, int sms, cudaStream_t s) {
   if (C == 80 || C == 64 || C == 128) {
     const int d_chunk = min(kBwdMaxChunk, ceil_div(p.D, 16) * 16);
     const size_t smem = bwd16_smem_bytes(d_chunk);  // <= 28 KB
-    if (C == 80) k_pool_bwd_pixels16<FeatT, 1, 1><<<grid16, 256, smem, s>>>(p, d_chunk);
-    else if (C == 64) k_pool_bwd_pixels16<FeatT, 1, 0><<<grid16, 256, smem, s>>>(p, d_chunk);
-    else k_pool_bwd_pixels16<FeatT, 2, 0><<<grid16, 256, smem, s>>>(p, d_chunk);
-    RCB_LAUNCH_CHECK();
+    if (C == 80) RCB_CUDA_TRY(launch_pdl(k_pool_bwd_pixels16<FeatT, 1, 1>, grid16, 256, smem, s, p, d_chunk));
+    else if (C == 64) RCB_CUDA_TRY(launch_pdl(k_pool_bwd_pixels16<FeatT, 1, 0>, grid16, 256, smem, s, p, d_chunk));
+    else RCB_CUDA_TRY(launch_pdl(k_pool_bwd_pixels16<FeatT, 2, 0>, grid16, 256, smem, s, p, d_chunk));
     return RCB_OK;
   }
   const int grid = max(1, min(ceil_div(p.n_pixels, 8), sms * 32));

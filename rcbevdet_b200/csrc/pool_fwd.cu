@@ -134,6 +134,7 @@ template <typename FeatT, int kC4>
 #endif
 __global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ? RCB_FWD_MINCTAS : 2) : 1)
     k_pool_fwd_tile(FwdTileParams p) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C4 = kC4 ? kC4 : p.C4;
   const int C = C4 * 4;
@@ -350,8 +351,7 @@ static int launch_tile_c4(const rcb_pool_desc *d, FwdTileParams &p, cudaStream_t
   RCB_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd_tile<FeatT, kC4>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long grid = (long long)d->B * p.tiles_r * p.tiles_x;
-  k_pool_fwd_tile<FeatT, kC4><<<(unsigned)grid, threads, smem, s>>>(p);
-  RCB_LAUNCH_CHECK();
+  RCB_CUDA_TRY(launch_pdl(k_pool_fwd_tile<FeatT, kC4>, (unsigned)grid, threads, smem, s, p));
   return RCB_OK;
 }
 
