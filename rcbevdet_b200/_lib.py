@@ -9,7 +9,8 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "librcbevdet_b200.so")
+# RCB_LIB_PATH selects another build of the SAME library (kernel experiments, tools/build_variant.sh)
+LIB_PATH = os.environ.get("RCB_LIB_PATH") or os.path.join(_PKG, "lib", "librcbevdet_b200.so")
 
 RCB_OK = 0
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
