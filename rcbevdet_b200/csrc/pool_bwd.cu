@@ -296,8 +296,9 @@ __global__ void __launch_bounds__(256, 4) k_pool_bwd_pixels16(BwdPixelParams p, 
           for (int t = 0; t < 2; ++t) {
             float s = 0.f;
             if (cells[t] >= 0) {
-              const unsigned row_off = (unsigned)cells[t] * (unsigned)(kC * 4);
-              const char *row = og_lane + row_off;
+              // one IMAD.WIDE each: 32-bit cell index x row bytes + pinned 64-bit lane base
+              const char *row = og_lane + (size_t)(unsigned)cells[t] * (size_t)(kC * 4);
+              const char *tail = og_tail + (size_t)(unsigned)cells[t] * (size_t)(kC * 4);
               const float2 ww = make_float2(ws[t], ws[t]);
               float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(256, 4) k_pool_bwd_pixels16(BwdPixelParams p, 
 #pragma unroll
               for (int j = 0; j < kNS; ++j) {
                 // scalar tail: channel 64*kNQ + 16*j + l16
-                const float g = __ldg(reinterpret_cast<const float *>(og_tail + row_off + 64 * j));
+                const float g = __ldg(reinterpret_cast<const float *>(tail + 64 * j));
                 s = fmaf(g, fs[j], s);
                 gs[j] = fmaf(g, ws[t], gs[j]);
               }
