@@ -130,7 +130,7 @@ template <typename FeatT, int kC4>
 #define RCB_FWD_MINCTAS 4  // measured: 3 -> 104 us, 4 -> 99 us, 5+ -> no gain (the row loads need the registers)
 #endif
 #ifndef RCB_FWD_UNROLL
-#define RCB_FWD_UNROLL 8
+#define RCB_FWD_UNROLL 6  // with the lane base pinned: 6 -> 96.4 us, 7 -> 97.0, 8 -> 99.1 (spills at 48 registers)
 #endif
 __global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ? RCB_FWD_MINCTAS : 2) : 1)
     k_pool_fwd_tile(FwdTileParams p) {
@@ -198,6 +198,9 @@ __global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ?
 
   const int group = tid / C4, q = tid - group * C4;
   const char *feat_q = static_cast<const char *>(p.feat) + (size_t)q * 4 * sizeof(FeatT);
+  // pin the full per-lane base in a register pair: otherwise the compiler keeps q * 16 and re-adds
+  // the uniform tensor base with a 64-bit IADD3 pair in front of EVERY row load
+  asm volatile("" : "+l"(feat_q));
   const unsigned row_stride = (unsigned)C * sizeof(FeatT);
   // combine / write role: lane <-> cell, this warp's quads are warp and warp + n_warps
   float4 racc[2];
