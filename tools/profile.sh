@@ -3,7 +3,7 @@
 # usage: tools_profile.sh <tag>
 TAG=${1:-r01}
 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --profile > gpurun_out/plain_$TAG.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 27 -c 36 --csv --log-file gpurun_out/launches_$TAG.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 29 -c 36 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline --profile > gpurun_out/ncu_launch_$TAG.log 2>&1
 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --profile > gpurun_out/plain2_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on \
