@@ -235,10 +235,14 @@ __global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ?
         }
       }
     }
-    // ---- work items: every cell is cut into pieces of <= L points, L >= n / kGroups ----------
-    const int L = max(kMinItem, ceil_div(n, kGroups));
+    // ---- work items: every cell is cut into equal pieces of <= L points -----------------------
     if (tid < 32) {
       const int a = max(cell_lo[tid], cb), bnd = min(cell_hi[tid], cb + n);
+      // as many items as the part buffer holds (non-empty cells + extra cuts <= kMaxItems), but no
+      // shorter than kMinItem points: a dense round (7 cells x 190 points) becomes ~40 pieces of 32
+      // instead of 20 of 64, which the 16 lane-groups share far more evenly
+      const int n_cells_here = __popc(__ballot_sync(kFull, bnd > a));
+      const int L = max(kMinItem, ceil_div(n, max(kGroups, kMaxItems - n_cells_here)));
       const int mine = bnd > a ? ceil_div(bnd - a, L) : 0;
       int incl = mine;
 #pragma unroll
@@ -249,9 +253,12 @@ __global__ void __launch_bounds__(kC4 ? kC4 * kGroups : 1024, kC4 ? (kC4 <= 20 ?
       int off = incl - mine;
       cell_item0[tid] = off;
       if (tid == 31) cell_item0[32] = incl;
+      // equal pieces (a 190-point cell with L = 80 becomes 64+63+63, not 80+80+30): the round ends
+      // with its longest lane-group
+      const int piece = mine > 0 ? ceil_div(bnd - a, mine) : 0;
       for (int k = 0; k < mine; ++k, ++off) {
-        item_lo[off] = a + k * L - cb;
-        item_hi[off] = min(bnd, a + (k + 1) * L) - cb;
+        item_lo[off] = a + k * piece - cb;
+        item_hi[off] = min(bnd, a + (k + 1) * piece) - cb;
       }
     }
     __syncthreads();
