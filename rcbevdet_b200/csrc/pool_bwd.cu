@@ -150,25 +150,25 @@ __global__ void __launch_bounds__(256) k_pool_bwd_pixels(BwdPixelParams p) {
 // ---------------------------------------------------------------------------------------------
 template <int kSlots>
 __device__ __forceinline__ float transpose_reduce16(float (&v)[kSlots], int l16) {
-  static_assert(kSlots == 8 || kSlots == 16, "slot tiers");
+  static_assert(kSlots == 4 || kSlots == 8 || kSlots == 16, "slot tiers");
 #pragma unroll
   for (int h = 8; h >= 1; h >>= 1) {
     constexpr int kTop = kSlots;
     const int n = (kTop * h) / 16;  // values still held per lane after this step
-    if (n == 0) {  // kSlots == 8, h == 1: both lanes of a pair hold the same slot
-      v[0] += __shfl_xor_sync(kFull, v[0], 1);
-      break;
-    }
+    if (n == 0) {  // fewer slots than lanes: the lanes of a pair hold the same slot
+      v[0] += __shfl_xor_sync(kFull, v[0], h);
+    } else {
 #pragma unroll
-    for (int k = 0; k < kSlots / 2; ++k) {
-      if (k >= n) break;
-      const bool up = l16 & h;
-      const float send = up ? v[k] : v[k + n];
-      const float keep = up ? v[k + n] : v[k];
-      v[k] = keep + __shfl_xor_sync(kFull, send, h);
+      for (int k = 0; k < kSlots / 2; ++k) {
+        if (k >= n) break;
+        const bool up = l16 & h;
+        const float send = up ? v[k] : v[k + n];
+        const float keep = up ? v[k + n] : v[k];
+        v[k] = keep + __shfl_xor_sync(kFull, send, h);
+      }
     }
   }
-  return v[0];  // kSlots == 16: lane l holds slot l; kSlots == 8: lanes 2s and 2s + 1 hold slot s
+  return v[0];  // slot s ends up in the 16 / kSlots lanes starting at s * 16 / kSlots
 }
 
 template <typename T>
@@ -257,6 +257,10 @@ __global__ void __launch_bounds__(256, 4) k_pool_bwd_pixels16(BwdPixelParams p, 
       for (int d0 = 0; d0 < n_d; d0 += 16) {
         const int my_cell = s_cell[(d0 + l16) * kBwdTilePitch + px_mine];
         const float my_w = s_w[(d0 + l16) * kBwdTilePitch + px_mine];
+        if (__ballot_sync(kFull, my_cell >= 0) == 0u) {  // all 32 bins dropped (rays that left the grid)
+          s_dg[(d0 + l16) * kBwdTilePitch + px_mine] = 0.f;
+          continue;
+        }
         // Consecutive depth bins of a pixel often fall into the same BEV cell (1.42 bins per (cell,
         // pixel) pair on average: a ray crosses a 0.8 m cell in ~1.6 steps of 0.5 m).  Such a run
         // shares its out_grad row and its dot product, so only the run's first bin (at most 4 bins
@@ -327,7 +331,13 @@ __global__ void __launch_bounds__(256, 4) k_pool_bwd_pixels16(BwdPixelParams p, 
         // a bin's value sits in the slot of its group head: slot = rank of the head lane among the heads
         const int my_slot = __popc(heads16 & ((1u << head_lane) - 1u));
         float total;
-        if (n_heads_max <= 8) {  // warp-uniform
+        if (n_heads_max <= 4) {  // warp-uniform tiers: fewer predicated bodies, shorter reduction
+          float dot[4];
+#pragma unroll
+          for (int k2 = 0; k2 < 2; ++k2) slot_pair(k2, dot[2 * k2], dot[2 * k2 + 1]);
+          total = transpose_reduce16<4>(dot, l16);
+          total = __shfl_sync(kFull, total, 4 * my_slot, 16);
+        } else if (n_heads_max <= 8) {
           float dot[8];
 #pragma unroll
           for (int k2 = 0; k2 < 4; ++k2) slot_pair(k2, dot[2 * k2], dot[2 * k2 + 1]);
