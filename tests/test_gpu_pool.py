@@ -80,7 +80,7 @@ def test_prepare_then_pool_forward_backward(aug):
     # untouched cells are exactly zero
     empty = np.ones(shape[0] * shape[1] * shape[2] * shape[3], bool)
     empty[ranks[0]] = False
-    assert float(bev.permute(0, 2, 3, 4, 1).reshape(-1, shape[4])[torch.from_numpy(empty).cuda()].abs().max()) == 0.0
+    assert float(bev.detach().permute(0, 2, 3, 4, 1).reshape(-1, shape[4])[torch.from_numpy(empty).cuda()].abs().max()) == 0.0
     # backward
     gen = torch.Generator().manual_seed(3)
     og = torch.randn(bev.shape, generator=gen)
@@ -93,6 +93,37 @@ def test_prepare_then_pool_forward_backward(aug):
     kept = np.zeros(depth.numel(), bool)
     kept[ranks[1]] = True
     assert float(d.grad.flatten()[torch.from_numpy(~kept).cuda()].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("C,depth_cfg,input_size,B", [
+    (80, (1.0, 60.0, 0.35), (128, 352), 1),   # D = 169: the backward stages its depth columns in two chunks
+    (64, (1.0, 60.0, 1.0), (112, 208), 1),    # one quad per lane, 546 pixels: a partial 16-pixel group
+    (128, (1.0, 60.0, 2.0), (112, 208), 2),   # two quads per lane
+    (96, (1.0, 60.0, 2.0), (128, 352), 1),    # channel count without a half-warp kernel: 32-lane fallback
+    (80, (1.0, 8.0, 0.5), (112, 208), 1),     # D = 14 < 16: a single partial batch
+])
+def test_backward_kernel_variants(C, depth_cfg, input_size, B):
+    """Every structured-backward code path (channel templates, chunked depth staging, ragged pixel
+    groups) and the forward for the same channel counts, against the oracle."""
+    import rcbevdet_b200 as rcb
+    from rcbevdet_b200 import rig
+    grid = rig.R50_GRID
+    coor, depth, feat = _case(B=B, depth_cfg=depth_cfg, input_size=input_size, C=C, seed=C)
+    ranks, shape, feat_rows, want = _oracle_pool(coor, depth, feat, grid)
+    if ranks[0] is None:
+        pytest.skip("geometry keeps no point")
+    lo, iv, sz = rig.grid_tensors(grid)
+    rb, rd, rf, st, ln = rcb.voxel_pooling_prepare_v2(coor.cuda(), lo, iv, sz)
+    d = depth.cuda().requires_grad_(True)
+    f = feat.cuda().requires_grad_(True)
+    bev = rcb.bev_pool_v2(d, f.permute(0, 1, 3, 4, 2), rd, rf, rb, shape, st, ln)
+    _close(bev, oracle.to_bczyx(want), RTOL32, "bev")
+    og = torch.randn(bev.shape, generator=torch.Generator().manual_seed(C + 1))
+    bev.backward(og.cuda())
+    og_rows = og.permute(0, 2, 3, 4, 1).contiguous().numpy()
+    dg, fg = oracle.bev_pool_v2_backward(og_rows, depth.numpy(), feat_rows, ranks[1], ranks[2], ranks[0], threads=8)
+    _close(d.grad, dg, RTOL32, "depth_grad")
+    _close(f.grad.permute(0, 1, 3, 4, 2), fg, RTOL32, "feat_grad")
 
 
 def test_quickcumsum_channels_last_and_determinism():
