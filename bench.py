@@ -489,6 +489,11 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly one JSON line: libraries that print to file descriptor 1 (NCCL's version
+    # banner does, whatever NCCL_DEBUG_FILE says) are sent to stderr, Python keeps the real stdout
+    sys.stdout.flush()
+    sys.stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
