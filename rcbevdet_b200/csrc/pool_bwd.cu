@@ -5,15 +5,17 @@
 //   depth_grad[ranks_depth[p]]   = sum_c out_grad[ranks_bev[p], c] * feat[ranks_feat[p], c]
 //   feat_grad[ranks_feat[p], c] += out_grad[ranks_bev[p], c] * depth[ranks_depth[p]]
 //
-//  k_pool_bwd_pixels (structured ranks: ranks_depth unique, ranks_feat = pixel of ranks_depth --
-//      what prepare emits): no sort at all.  The points of pixel (b, n, h, w) are the D depth bins
-//      of that pixel, and the inverse map point_cell[P] (BEV cell of each frustum point, -1 =
-//      dropped; a by-product of prepare) says where each went.  One warp per pixel keeps the
-//      pixel's context row in registers, walks its depth column 32 bins at a time, gathers the
-//      out_grad row of each kept bin with one 128-bit load per lane, and produces both gradients:
-//      feat_grad accumulates in registers (written once, zeros for unseen pixels), depth_grad is a
-//      32-way transposed warp reduction (31 shuffles per 32 bins instead of 5 per bin).  Both
-//      outputs are fully written, deterministic, no atomics, no memset.
+//  Structured ranks (ranks_depth unique, ranks_feat = pixel of ranks_depth -- what prepare emits):
+//      no sort at all.  The points of pixel (b, n, h, w) are the D depth bins of that pixel, and
+//      the inverse map point_cell[P] (BEV cell of each frustum point, -1 = dropped; a by-product
+//      of prepare) says where each went.  A pixel's context row stays in registers while its depth
+//      column is walked; every kept bin gathers its out_grad row; feat_grad accumulates in
+//      registers (written once, zeros for unseen pixels), depth_grad is a transposed warp
+//      reduction of the per-bin dot products.  Both outputs are fully written, deterministic, no
+//      atomics, no memset.
+//      k_pool_bwd_pixels16 (C = 64 / 80 / 128, the hot one): 16 lanes per pixel, 16 pixels per
+//      CTA, columns staged through shared memory, merged (cell, pixel) runs -- see its comment.
+//      k_pool_bwd_pixels (other C): one warp per pixel, 32 bins at a time.
 //
 //  k_pool_bwd_points (general ranks): one warp per point; depth_grad exact, feat_grad by float
 //      atomics into a zero-filled buffer.
