@@ -11,8 +11,9 @@ exactly what a training step of the reference runs with accelerate=False
 (mmdet3d/models/necks/view_transformer.py:180-205, mmdet3d/ops/bev_pool_v2/bev_pool.py).
 Weak scaling: every rank pools its own 8 samples, no collective on the data path.
 
-Rank 0 prints ONE JSON line.  `value` = samples/s with inputs resident in HBM (CUDA events, max
-over ranks); `e2e` = the same step through the public API from pinned HOST buffers, host<->device
+Rank 0 prints ONE JSON line (everything else any library writes to stdout is sent to stderr).
+`value` = samples/s with inputs resident in HBM (CUDA events around the K timed steps, max over
+ranks; per-stage events on every 8th step only, they cost ~18 us per step); `e2e` = the same step through the public API from pinned HOST buffers, host<->device
 copies inside the timed region; `roofline` = the dominant kernel against the measured HBM peak;
 `cpu_baseline` = the CPU oracle (C, OpenMP) timed on this box's host cores (N=1, rank 0).
 `--impl reference` times that CPU implementation alone (the reference has no CPU pool kernel;
