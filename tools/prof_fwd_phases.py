@@ -1,6 +1,7 @@
 import ctypes, sys, numpy as np, torch
 # Debug helper: per-CTA phase timeline of k_pool_fwd_tile.  Needs a build with -DRCB_PROFILE_PHASES
-# (add it to NVCC_FLAGS in rcbevdet_b200/build.py); run from the repo root on the GPU box.
+# (tools/build_variant.sh prof "-DRCB_PROFILE_PHASES", then RCB_LIB_PATH=rcbevdet_b200/lib/variants/lib_prof.so);
+# run from the repo root on the GPU box.
 sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import bench
 from rcbevdet_b200 import _lib, rig
