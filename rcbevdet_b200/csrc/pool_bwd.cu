@@ -244,15 +244,28 @@ __global__ void __launch_bounds__(256, 4) k_pool_bwd_pixels16(BwdPixelParams p, 
 
     for (int dc0 = 0; dc0 < p.D; dc0 += d_chunk) {
       const int n_d = min(d_chunk, p.D - dc0);
-      for (int d = threadIdx.x >> 4; d < d_chunk; d += 16) {
-        int c = -1;
-        float w = 0.f;
-        if (live_l && d < n_d) {
-          c = __ldg(p.point_cell + col_l + (dc0 + d) * p.HW);
-          w = __ldg(p.depth + col_l + (dc0 + d) * p.HW);
+      // eight depth bins per thread and step, all sixteen loads issued before the first store (the
+      // trip count is a run-time value: left alone, the loop keeps two loads in flight per trip)
+      for (int ds = threadIdx.x >> 4; ds < d_chunk; ds += 128) {
+        int c8[8];
+        float w8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int d = ds + 16 * u;
+          c8[u] = -1, w8[u] = 0.f;
+          if (live_l && d < n_d) {
+            c8[u] = __ldg(p.point_cell + col_l + (dc0 + d) * p.HW);
+            w8[u] = __ldg(p.depth + col_l + (dc0 + d) * p.HW);
+          }
         }
-        s_cell[d * kBwdTilePitch + px_load] = c;
-        s_w[d * kBwdTilePitch + px_load] = w;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int d = ds + 16 * u;
+          if (d < d_chunk) {
+            s_cell[d * kBwdTilePitch + px_load] = c8[u];
+            s_w[d * kBwdTilePitch + px_load] = w8[u];
+          }
+        }
       }
       __syncthreads();
 
