@@ -82,6 +82,13 @@ int rcb_voxel_pooling_prepare_v2(const rcb_prepare_desc *d, const float *coor, i
                                  int *counts, void *workspace, size_t workspace_bytes, int device,
                                  rcb_stream_t stream);
 
+/* Test hook (synchronous, allocates 16 bytes itself): the kernels replace the fp32 division of
+ * view_transformer.py:231 by a reciprocal-based sequence that must round identically.  Sweeps all
+ * 2^32 numerators for one divisor; *mismatches = quotients that differ from IEEE division in any
+ * bit, *first_bad_plus_1 = bit pattern of the first such numerator + 1 (0 when none). */
+int rcb_debug_exactdiv_sweep(float divisor, unsigned long long *mismatches,
+                             unsigned long long *first_bad_plus_1, int device);
+
 /* ------------------------------------------------------------------------------------------
  * Rows F, B, L -- bev_pool_v2_forward / bev_pool_v2_backward
  *   (mmdet3d/ops/bev_pool_v2/src/bev_pool.cpp:30-57, 74-104; kernels bev_pool_cuda.cu:21-48, 67-121)

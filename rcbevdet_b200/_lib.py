@@ -43,6 +43,8 @@ SIGNATURES = {
     "rcb_device_info": (_i, [_i] + [ctypes.POINTER(ctypes.c_int)] * 4),
     "rcb_prepare_workspace_bytes": (_sz, [ctypes.POINTER(PrepareDesc)]),
     "rcb_voxel_pooling_prepare_v2": (_i, [ctypes.POINTER(PrepareDesc)] + [_vp] * 9 + [_vp, _sz, _i, _vp]),
+    "rcb_debug_exactdiv_sweep": (_i, [ctypes.c_float, ctypes.POINTER(ctypes.c_ulonglong),
+                                      ctypes.POINTER(ctypes.c_ulonglong), _i]),
     "rcb_pool_validate_workspace_bytes": (_sz, [ctypes.POINTER(PoolDesc)]),
     "rcb_pool_validate": (_i, [ctypes.POINTER(PoolDesc)] + [_vp] * 7 + [_vp, _sz, _i, _vp]),
     "rcb_pool_build_cellmap": (_i, [ctypes.POINTER(PoolDesc), _vp, _vp, _vp, _i, _vp]),

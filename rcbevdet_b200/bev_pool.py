@@ -30,10 +30,6 @@ def _require_cuda(t, name):
         raise RuntimeError(f"bev_pool_v2: `{name}` must be a CUDA tensor; rcbevdet_b200 has no CPU fallback")
 
 
-def _ranks(t):
-    return t.int().contiguous()  # bev_pool.py:18,22-25
-
-
 def feat_rows(feat):
     """Context features as contiguous channels-last rows (n_pixels, C).
 
@@ -85,18 +81,19 @@ def _forward(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, in
     dev = depth.device
     depth = depth.detach().contiguous().float()          # bev_pool.py:19
     rows = feat_rows(feat.detach())                      # bev_pool.py:20
-    ranks_depth, ranks_feat, ranks_bev = _ranks(ranks_depth), _ranks(ranks_feat), _ranks(ranks_bev)
-    interval_starts, interval_lengths = _ranks(interval_starts), _ranks(interval_lengths)
     if not (ranks_depth.numel() == ranks_feat.numel() == ranks_bev.numel()):
         raise ValueError("ranks_depth, ranks_feat and ranks_bev must have the same length")
     if interval_starts.numel() != interval_lengths.numel():
         raise ValueError("interval_starts and interval_lengths must have the same length")
+    originals = (ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths)
     desc = _pool_desc(depth, rows, ranks_depth, interval_lengths, bev_feat_shape, layout)
     n_cells = desc.B * desc.Z * desc.Y * desc.X
-    plan = _plan.lookup(ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths, n_cells,
-                        desc.n_depth)
+    # the plan is keyed on the caller's own tensors; int64 / strided ranks are converted to int32
+    # once, inside the plan (bev_pool.py:18,22-25 converts on every call)
+    plan = _plan.lookup(*originals, n_cells, desc.n_depth)
     if plan is None:
-        plan = _plan.derive(desc, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths)
+        plan = _plan.derive(desc, originals)
+    ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths = plan.ranks
     desc.flags = plan.flags
     if plan.structured:
         desc.D, desc.HW = plan.D, plan.HW

@@ -477,7 +477,8 @@ extern "C" int rcb_bev_pool_v2_bwd(const rcb_pool_desc *d, const float *out_grad
                           d->HW > 0 && (d->C % 4) == 0 && d->C <= 256 &&
                           (((uintptr_t)feat) % (4 * elem)) == 0 && (((uintptr_t)og_rows) % 16) == 0 &&
                           (((uintptr_t)feat_grad) % 16) == 0 &&
-                          (long long)d->n_pixels * d->D == (long long)d->n_depth;
+                          (long long)d->n_pixels * d->D == (long long)d->n_depth &&
+                          d->n_pixels % d->HW == 0;  // whole camera images: col + d*HW stays inside n_depth
   if (structured) {
     BwdPixelParams p;
     p.out_grad_rows = og_rows, p.depth = depth, p.feat = feat, p.point_cell = point_cell;

@@ -49,7 +49,9 @@ __global__ void __launch_bounds__(256)
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_intervals; i += stride) {
     const int s = starts[i], l = lengths[i];
     const int expect_end = (i + 1 < n_intervals) ? starts[i + 1] : n_points;
-    if (l <= 0 || s < 0 || s >= n_points || (i == 0 && s != 0) || s + l != expect_end) {
+    // l <= n_points - s first: it bounds the scan below even when starts[i + 1] is garbage, and keeps
+    // s + l from overflowing
+    if (l <= 0 || s < 0 || s >= n_points || l > n_points - s || (i == 0 && s != 0) || s + l != expect_end) {
       bad_local |= RCB_PLAN_INTERVALS_OK | RCB_PLAN_SORTED_CELLS;
       continue;
     }

@@ -25,9 +25,10 @@ class PoolPlan:
     unless SORTED_CELLS).  point_cell: int32 [n_depth] BEV cell of each depth element, -1 if
     unused (None unless STRUCTURED).  D / HW describe the frustum when STRUCTURED."""
 
-    __slots__ = ("flags", "cell_start", "point_cell", "D", "HW", "n_cells", "n_depth", "keys", "hold")
+    __slots__ = ("flags", "cell_start", "point_cell", "D", "HW", "n_cells", "n_depth", "keys", "hold", "ranks")
 
-    def __init__(self, flags, cell_start, point_cell, D, HW, n_cells, n_depth, keys=None, hold=None):
+    def __init__(self, flags, cell_start, point_cell, D, HW, n_cells, n_depth, keys=None, hold=None,
+                 ranks=None):
         self.flags = int(flags)
         self.cell_start = cell_start
         self.point_cell = point_cell
@@ -37,6 +38,10 @@ class PoolPlan:
         self.n_depth = int(n_depth)
         self.keys = keys
         self.hold = hold
+        # the five rank arrays as int32 contiguous tensors (what the kernels read); for ranks that
+        # arrive as int64 / strided views these are converted ONCE and kept here, so the cache hits
+        # on the caller's own tensors instead of on a fresh copy per call
+        self.ranks = ranks
 
     @property
     def sorted_cells(self):
@@ -48,11 +53,15 @@ class PoolPlan:
 
 
 def _key(t):
-    return (t.data_ptr(), t.numel(), t._version, t.dtype, t.device)
+    # tensors created under torch.inference_mode() do not track a version counter (reading
+    # `_version` raises); they are immutable outside inference mode, so 0 is as good a version
+    version = 0 if t.is_inference() else t._version
+    return (t.data_ptr(), t.numel(), version, t.dtype, t.device, tuple(t.stride()))
 
 
 def attach(plan, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths):
     plan.keys = tuple(_key(t) for t in (ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths))
+    plan.ranks = (ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths)
     for t in (ranks_depth, ranks_bev):
         setattr(t, _ATTR, plan)
 
@@ -80,8 +89,21 @@ def lookup(ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths
     return plan
 
 
-def derive(desc, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths):
-    """Validate foreign ranks on the device (one flag read-back) and cache the result."""
+def _as_kernel_ranks(t):
+    import torch as _t
+    return t if (t.dtype == _t.int32 and t.is_contiguous()) else t.int().contiguous()  # bev_pool.py:18,22-25
+
+
+def derive(desc, originals):
+    """Validate foreign ranks on the device (one flag read-back) and cache the result under the
+    identity of the caller's ORIGINAL tensors (ranks_depth, ranks_feat, ranks_bev, interval_starts,
+    interval_lengths); int64 / strided ranks are converted to int32 once and kept in the plan.
+
+    The cache key is (data_ptr, numel, version counter, dtype, strides): ranks must not be modified
+    behind the version counter (`.data.copy_`, external kernels) while a plan is cached -- call
+    clear_cache() after such a write."""
+    ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths = (
+        _as_kernel_ranks(t) for t in originals)
     dev = ranks_depth.device if ranks_depth.numel() else ranks_bev.device
     n_cells = desc.B * desc.Z * desc.Y * desc.X
     lib = _lib.lib()
@@ -107,9 +129,9 @@ def derive(desc, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_l
     if not flags & _lib.PLAN_STRUCTURED:
         point_cell = None
     tensors = (ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths)
-    keys = tuple(_key(t) for t in tensors)
+    keys = tuple(_key(t) for t in originals)
     plan = PoolPlan(flags, cell_start, point_cell, desc.D, desc.HW, n_cells, desc.n_depth, keys=keys,
-                    hold=tensors)  # holding the tensors keeps their addresses from being reused
+                    hold=tuple(originals), ranks=tensors)  # holding the tensors keeps their addresses from being reused
     with _cache_lock:
         _cache[(keys, n_cells, desc.n_depth)] = plan
         while len(_cache) > _CACHE_MAX:

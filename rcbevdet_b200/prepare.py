@@ -54,6 +54,8 @@ def prepare_async(coor, grid_lower_bound, grid_interval, grid_size):
     if coor.dtype != torch.float32:
         coor = coor.float()
     coor = coor.contiguous()
+    if coor.data_ptr() % 16:                 # an offset view: the kernels fetch 16-byte quads
+        coor = coor.clone()
     dev = coor.device
     lib = _lib.lib()
     P = desc.B * desc.N * desc.D * desc.H * desc.W

@@ -53,10 +53,34 @@ class _ViewPool(torch.autograd.Function):
         return depth_grad, feat_grad, None
 
 
+def fused_path_supports(C):
+    """The sync-free chain drives the CSR (cell-stationary) forward kernel, which owns whole
+    128-bit channel quads: C % 8 == 0 and C <= 256.  Any other channel count (the reference
+    accepts every C) takes the two-call route below, which reads the counts back once."""
+    return C % 8 == 0 and 0 < C <= 256
+
+
 def voxel_pooling_v2(coor, depth, feat, grid_lower_bound, grid_interval, grid_size, collapse_z=True,
                      return_prepared=False):
     """coor (B,N,D,H,W,3) fp32; depth (B,N,D,H,W); feat (B,N,C,H,W) -- exactly the arguments of
     the reference method.  Returns bev_feat (B, C*Z, Y, X) (collapse_z) or (B,C,Z,Y,X)."""
+    C = int(feat.shape[2])
+    if not fused_path_supports(C):
+        # view_transformer.py:180-205 literally: prepare (one read-back of the counts), then the op
+        # through its general kernels, with the real n_kept / n_intervals
+        from .prepare import voxel_pooling_prepare_v2
+        if return_prepared:
+            raise ValueError("return_prepared needs the fused path (C % 8 == 0, C <= 256)")
+        rb, rd, rf, st, ln = voxel_pooling_prepare_v2(coor, grid_lower_bound, grid_interval, grid_size)
+        B = int(coor.shape[0])
+        gx, gy, gz = (int(float(v)) for v in (grid_size.tolist() if isinstance(grid_size, torch.Tensor)
+                                              else grid_size))
+        if rb is None:                                           # :184-194
+            bev = torch.zeros((B, C, gz, gy, gx), dtype=torch.float32, device=depth.device)
+            bev = bev + 0.0 * (depth.sum() + feat.sum())         # keep the graph connected
+        else:
+            bev = _bp.bev_pool_v2(depth, feat.permute(0, 1, 3, 4, 2), rd, rf, rb, (B, gz, gy, gx, C), st, ln)
+        return torch.cat(bev.unbind(dim=2), 1) if collapse_z else bev
     prepared = prepare_async(coor, grid_lower_bound, grid_interval, grid_size)
     feat = feat.permute(0, 1, 3, 4, 2)                       # view_transformer.py:195
     bev = _ViewPool.apply(depth, feat, prepared)
