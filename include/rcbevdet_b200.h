@@ -46,7 +46,8 @@ typedef struct CUstream_st *rcb_stream_t; /* == cudaStream_t */
 #define RCB_PLAN_INTERVALS_OK 2   /* intervals tile [0, n_points) contiguously, lengths > 0           */
 #define RCB_PLAN_SORTED_CELLS 4   /* interval cells strictly increasing -> zero-filling tile kernel    */
 #define RCB_PLAN_STRUCTURED 8     /* ranks_depth unique and ranks_feat == pixel_of(ranks_depth)        */
-#define RCB_PLAN_ALL 15
+#define RCB_PLAN_SAMPLE_LOCAL 16  /* ranks_feat[i] lies in the sample of ranks_bev[i] -> row-staging forward */
+#define RCB_PLAN_ALL 31
 
 int rcb_version(void);
 const char *rcb_error_string(int code);

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("RCB_LIB_PATH") or os.path.join(_PKG, "lib", "librcbev
 RCB_OK = 0
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 LAYOUT_CELLS_C, LAYOUT_B_C_CELLS = 0, 1
-PLAN_RANGES_OK, PLAN_INTERVALS_OK, PLAN_SORTED_CELLS, PLAN_STRUCTURED, PLAN_ALL = 1, 2, 4, 8, 15
+PLAN_RANGES_OK, PLAN_INTERVALS_OK, PLAN_SORTED_CELLS, PLAN_STRUCTURED, PLAN_SAMPLE_LOCAL, PLAN_ALL = 1, 2, 4, 8, 16, 31
 
 
 class PrepareDesc(ctypes.Structure):

@@ -22,6 +22,8 @@
 //
 //  k_pool_fwd_intervals (general path, any ranks the reference accepts): one warp per interval,
 //      writes only non-empty cells into a pre-zeroed `out`.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rcb {
@@ -387,6 +389,19 @@ static int launch_intervals(const rcb_pool_desc *d, const float *depth, const vo
   return RCB_OK;
 }
 
+bool fwd_rows_eligible(const rcb_pool_desc *d, const void *feat, const int *cell_start);
+int fwd_rows_launch(const rcb_pool_desc *d, const float *depth, const void *feat, const int *ranks_depth,
+                    const int *ranks_feat, const int *cell_start, float *out, cudaStream_t s);
+
+// Diagnostic knob (A/B timing only): RCB_FWD_KERNEL=tile keeps round 1's L1-gather kernel.
+static bool fwd_rows_disabled() {
+  static const bool off = [] {
+    const char *v = getenv("RCB_FWD_KERNEL");
+    return v != nullptr && v[0] == 't';
+  }();
+  return off;
+}
+
 int check_pool_desc(const rcb_pool_desc *d) {
   if (!d) return RCB_ERR_ARG;
   if (d->n_points < 0 || d->n_intervals < 0 || d->C <= 0 || d->B <= 0 || d->Z <= 0 || d->Y <= 0 ||
@@ -417,6 +432,10 @@ extern "C" int rcb_bev_pool_v2_fwd(const rcb_pool_desc *d, const float *depth, c
   const int cps = d->Z * d->Y * d->X;
   const size_t out_bytes = (size_t)d->B * cps * d->C * 4;
 
+  if (!fwd_rows_disabled() && fwd_rows_eligible(d, feat, cell_start)) {
+    if (d->n_points > 0 && (!depth || !feat || !ranks_depth || !ranks_feat)) return RCB_ERR_ARG;
+    return fwd_rows_launch(d, depth, feat, ranks_depth, ranks_feat, cell_start, out, s);
+  }
   const int elem = d->feat_dtype == RCB_DTYPE_F32 ? 4 : 2;
   const bool tile_ok = cell_start != nullptr && (d->C % 8) == 0 && d->C <= 256 && (long long)d->n_pixels * d->C * elem < (1ll << 32) &&
                        (((uintptr_t)feat) % (4 * elem)) == 0;
