@@ -47,7 +47,8 @@ typedef struct CUstream_st *rcb_stream_t; /* == cudaStream_t */
 #define RCB_PLAN_SORTED_CELLS 4   /* interval cells strictly increasing -> zero-filling tile kernel    */
 #define RCB_PLAN_STRUCTURED 8     /* ranks_depth unique and ranks_feat == pixel_of(ranks_depth)        */
 #define RCB_PLAN_SAMPLE_LOCAL 16  /* ranks_feat[i] lies in the sample of ranks_bev[i] -> row-staging forward */
-#define RCB_PLAN_ALL 31
+#define RCB_PLAN_PIXEL_MAJOR 32   /* inside a cell ranks_feat never decreases -> cursor walk, merged depth bins      */
+#define RCB_PLAN_ALL 63
 
 int rcb_version(void);
 const char *rcb_error_string(int code);
@@ -70,7 +71,8 @@ size_t rcb_prepare_workspace_bytes(const rcb_prepare_desc *d);
 /*
  * Outputs (all int32, device):
  *   ranks_bev / ranks_depth / ranks_feat : capacity P = B*N*D*H*W, first n_kept valid, sorted
- *       by ranks_bev with ascending ranks_depth inside a cell (the stable order).
+ *       by ranks_bev; inside a cell by (ranks_feat, depth bin), i.e. the depth bins of one camera
+ *       pixel are adjacent (the reference's argsort leaves this order unspecified).
  *   interval_starts / interval_lengths   : capacity min(P, B*gx*gy*gz), first n_intervals valid.
  *   point_cell  [P]            : global BEV cell of every frustum point, -1 if dropped
  *                                (the inverse map the backward pass uses).
@@ -82,6 +84,35 @@ int rcb_voxel_pooling_prepare_v2(const rcb_prepare_desc *d, const float *coor, i
                                  int *interval_lengths, int *point_cell, int *cell_start,
                                  int *counts, void *workspace, size_t workspace_bytes, int device,
                                  rcb_stream_t stream);
+
+/*
+ * LSSViewTransformer.get_lidar_coor (view_transformer.py:115-157) fused into the
+ * prepare stage.  The frustum points are generated inside the first kernel from the calibration
+ * instead of being materialised as `coor` (12 bytes per point written, read back and -- end to end
+ * -- shipped over PCIe).  All pointers are device pointers, float32:
+ *   u [W], v [H], d [D] : the frustum template's axes (create_frustum, view_transformer.py:85-113:
+ *                         linspace(0, W_in-1, W), linspace(0, H_in-1, H), arange(*depth_cfg) or the
+ *                         SID bins)
+ *   cam [B*N][24]       : per camera  inverse(post_rots) 3x3 row-major | post_trans[3] |
+ *                         combine = sensor2ego[:3,:3] @ inverse(cam2imgs) 3x3 | sensor2ego[:3,3]
+ *   bda [B][9]          : the BEV augmentation 3x3, row-major
+ * Operation order per point (every product and sum separately rounded, rows as (m0*x + m1*y) + m2*z):
+ *   p = (u,v,d) - post_trans;  p = inv_post_rot * p;  p = (p.x*p.z, p.y*p.z, p.z);
+ *   p = combine * p + trans;  p = bda * p.
+ * The reference leaves this order to its BLAS (batched 3x3 matmul); outputs are otherwise those of
+ * rcb_voxel_pooling_prepare_v2 on the coor so defined.
+ */
+typedef struct {
+  const float *u, *v, *d;
+  const float *cam;
+  const float *bda;
+} rcb_frustum_desc;
+
+int rcb_voxel_pooling_prepare_from_calib(const rcb_prepare_desc *d, const rcb_frustum_desc *fr,
+                                         int *ranks_bev, int *ranks_depth, int *ranks_feat,
+                                         int *interval_starts, int *interval_lengths, int *point_cell,
+                                         int *cell_start, int *counts, void *workspace,
+                                         size_t workspace_bytes, int device, rcb_stream_t stream);
 
 /* Test hook (synchronous, allocates 16 bytes itself): the kernels replace the fp32 division of
  * view_transformer.py:231 by a reciprocal-based sequence that must round identically.  Sweeps all

@@ -15,13 +15,17 @@ LIB_PATH = os.environ.get("RCB_LIB_PATH") or os.path.join(_PKG, "lib", "librcbev
 RCB_OK = 0
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 LAYOUT_CELLS_C, LAYOUT_B_C_CELLS = 0, 1
-PLAN_RANGES_OK, PLAN_INTERVALS_OK, PLAN_SORTED_CELLS, PLAN_STRUCTURED, PLAN_SAMPLE_LOCAL, PLAN_ALL = 1, 2, 4, 8, 16, 31
+PLAN_RANGES_OK, PLAN_INTERVALS_OK, PLAN_SORTED_CELLS, PLAN_STRUCTURED, PLAN_SAMPLE_LOCAL, PLAN_PIXEL_MAJOR, PLAN_ALL = 1, 2, 4, 8, 16, 32, 63
 
 
 class PrepareDesc(ctypes.Structure):
     _fields_ = [("B", ctypes.c_int), ("N", ctypes.c_int), ("D", ctypes.c_int), ("H", ctypes.c_int),
                 ("W", ctypes.c_int), ("lower", ctypes.c_float * 3), ("interval", ctypes.c_float * 3),
                 ("size", ctypes.c_float * 3)]
+
+
+class FrustumDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("u", "v", "d", "cam", "bda")]
 
 
 class PoolDesc(ctypes.Structure):
@@ -43,6 +47,8 @@ SIGNATURES = {
     "rcb_device_info": (_i, [_i] + [ctypes.POINTER(ctypes.c_int)] * 4),
     "rcb_prepare_workspace_bytes": (_sz, [ctypes.POINTER(PrepareDesc)]),
     "rcb_voxel_pooling_prepare_v2": (_i, [ctypes.POINTER(PrepareDesc)] + [_vp] * 9 + [_vp, _sz, _i, _vp]),
+    "rcb_voxel_pooling_prepare_from_calib": (_i, [ctypes.POINTER(PrepareDesc), ctypes.POINTER(FrustumDesc)] +
+                                             [_vp] * 8 + [_vp, _sz, _i, _vp]),
     "rcb_debug_exactdiv_sweep": (_i, [ctypes.c_float, ctypes.POINTER(ctypes.c_ulonglong),
                                       ctypes.POINTER(ctypes.c_ulonglong), _i]),
     "rcb_pool_validate_workspace_bytes": (_sz, [ctypes.POINTER(PoolDesc)]),

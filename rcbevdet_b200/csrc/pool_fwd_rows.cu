@@ -51,6 +51,7 @@ struct FwdRowsParams {
   int B;
   int npix_sample;       // context rows (pixels) per sample
   int bw;                // bitmap words = ceil(npix_sample / 32)
+  int pixel_major;       // inside a cell the points ascend by pixel (what prepare emits): cursor walk
   int sh;                // slots per half of the row stage
   unsigned pitch;        // bytes between staged rows (row bytes + 16: conflict-free quads)
   unsigned row_bytes;    // C * sizeof(FeatT)
@@ -64,7 +65,8 @@ __host__ __device__ inline size_t fwd_rows_stage_bytes(int sh, unsigned pitch, i
   return stage < transpose ? transpose : stage;
 }
 __host__ __device__ inline size_t fwd_rows_smem_bytes(int sh, unsigned pitch, int bw, int C) {
-  return fwd_rows_stage_bytes(sh, pitch, C) + (size_t)kEMax * 8 + (size_t)kEMax * 2 + (size_t)bw * 8 + kRowsTabBytes;
+  return fwd_rows_stage_bytes(sh, pitch, C) + (size_t)kEMax * 8 + (size_t)kEMax * 2 + (size_t)bw * 8 +
+         (size_t)(kEMax / 32) * 4 + (size_t)(kEMax + 8) * 2 + kRowsTabBytes;
 }
 
 // i-th element of {c, c-1, c+1, c-2, c+2, ...} clipped to [0, n), c = n / 2
@@ -163,6 +165,32 @@ __device__ __forceinline__ void rows_accumulate(const uint2 *__restrict__ ent, i
   }
 }
 
+// Multi-round walk when the points of a cell ascend by pixel (= by slot): the points of round r are
+// a contiguous piece of the cell's list; `cur` remembers where the previous round stopped.
+template <typename FeatT>
+__device__ __forceinline__ void rows_accumulate_cursor(const uint2 *__restrict__ ent, int &cur, int e,
+                                                       const unsigned char *__restrict__ bufp, unsigned rbase,
+                                                       unsigned half_bytes, unsigned qoff0, unsigned qoff1,
+                                                       float4 &acc0, float4 &acc1) {
+  while (cur < e) {
+    uint2 ev[4];
+    int taken = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ev[u] = (cur + u < e) ? ent[cur + u] : make_uint2(0xffffffffu, 0u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned rel = ev[u].x - rbase;
+      if (rel < half_bytes) {
+        rows_fma(acc0, lds_row4<FeatT>(bufp + rel + qoff0), __uint_as_float(ev[u].y));
+        rows_fma(acc1, lds_row4<FeatT>(bufp + rel + qoff1), __uint_as_float(ev[u].y));
+        ++taken;
+      }
+    }
+    cur += taken;
+    if (taken < 4) break;
+  }
+}
+
 // kL > 0: lanes per cell known at compile time (blockDim.x == 32 * kL); 0: run time (p.L).
 template <typename FeatT, int kL>
 __global__ void __launch_bounds__(kL ? 32 * kL : 1024, kL ? (kL <= 10 ? 3 : (kL <= 16 ? 2 : 1)) : 1)
@@ -179,13 +207,17 @@ __global__ void __launch_bounds__(kL ? 32 * kL : 1024, kL ? (kL <= 10 ? 3 : (kL 
   unsigned short *upix = reinterpret_cast<unsigned short *>(ent + kEMax);  // [kEMax] slot -> pixel of the sample
   unsigned *bitmap = reinterpret_cast<unsigned *>(upix + kEMax);         // [bw]
   unsigned *wpre = bitmap + p.bw;                                        // [bw] slots before each word
-  int *tab = reinterpret_cast<int *>(wpre + p.bw);
+  unsigned *cs_bits = wpre + p.bw;                                       // [kEMax / 32] first point of a cell?
+  unsigned short *pos_map = reinterpret_cast<unsigned short *>(cs_bits + kEMax / 32);  // [kEMax + 8] raw -> merged index
+  int *tab = reinterpret_cast<int *>(pos_map + kEMax + 8);
   int *cell_lo = tab;        // [32] patch-local point range of every cell
   int *cell_hi = tab + 32;   // [32]
   int *seg_off = tab + 64;   // [kRowsTileY + 1] patch-local prefix of the row slices
   int *seg_g = tab + 72;     // [kRowsTileY] global start of each row slice
   unsigned *s_warp = reinterpret_cast<unsigned *>(tab + 80);  // [32] scan scratch
   unsigned *s_nslots = reinterpret_cast<unsigned *>(tab + 112);
+  int *new_lo = tab + 120;   // [32] chunk-local entry range of every cell after merging
+  int *new_hi = tab + 152;   // [32]
 
   // Launch order: patches nearest the grid centre first, samples interleaved (point density peaks
   // around the ego vehicle, so the long patches start at once).  Any order is correct.
@@ -225,7 +257,6 @@ __global__ void __launch_bounds__(kL ? 32 * kL : 1024, kL ? (kL <= 10 ? 3 : (kL 
   const int total = seg_off[kRowsTileY];
 
   const int cell = tid / L, l = tid - cell * L;
-  const int my_lo = cell_lo[cell], my_hi = cell_hi[cell];
   const unsigned qoff0 = (unsigned)l * 4u * (unsigned)sizeof(FeatT);
   const unsigned qoff1 = (unsigned)(l + L) * 4u * (unsigned)sizeof(FeatT);
   const int pix_base = b * p.npix_sample;
@@ -238,7 +269,15 @@ __global__ void __launch_bounds__(kL ? 32 * kL : 1024, kL ? (kL <= 10 ? 3 : (kL 
     const int n = min(kEMax, total - cb);
     // ---- A: points of the chunk -> (pixel of the sample, depth weight); mark the pixels ----------
     for (int i = tid; i < p.bw; i += T) bitmap[i] = 0u;
+    for (int i = tid; i < kEMax / 32; i += T) cs_bits[i] = 0u;
     __syncthreads();
+    if (tid < 32) {  // first point (inside this chunk) of every non-empty cell: a merged run never crosses it
+      const int lo = cell_lo[tid], hi = cell_hi[tid];
+      if (hi > lo && hi > cb && lo < cb + n) {
+        const int idx = max(lo, cb) - cb;
+        atomicOr(&cs_bits[idx >> 5], 1u << (idx & 31));
+      }
+    }
     for (int i0 = tid; i0 < n; i0 += 4 * T) {
       int g[4], rd[4], rf[4];
 #pragma unroll
@@ -316,15 +355,94 @@ __global__ void __launch_bounds__(kL ? 32 * kL : 1024, kL ? (kL <= 10 ? 3 : (kL 
       cp_async_commit();
     };
     stage_round(0);
-    // every point's pixel becomes the byte offset of its slot (overlaps the first copies)
-    for (int i = tid; i < n; i += T) {
+    auto off_of = [&](int i) -> unsigned {  // byte offset of the slot of raw point i
       const unsigned pl = ent[i].x;
       const unsigned wd = pl >> 5;
-      const unsigned slot = wpre[wd] + __popc(bitmap[wd] & ((1u << (pl & 31u)) - 1u));
-      ent[i].x = slot * p.pitch;
+      return (wpre[wd] + __popc(bitmap[wd] & ((1u << (pl & 31u)) - 1u))) * p.pitch;
+    };
+    if (kL > 0) {
+      // ---- merge: consecutive points of one cell that read the same row (the depth bins of one
+      // (cell, pixel) pair, adjacent in prepare's order) become ONE entry whose weight is the sum of
+      // their depth weights, added in point order.  Thread t owns raw points [t*per, (t+1)*per); a
+      // run belongs to the thread that owns its first point.  Everything is held in registers across
+      // the barrier, so the compaction happens in place.
+      constexpr int kPer = kL > 0 ? (kEMax + 32 * kL - 1) / (32 * kL) : 1;
+      auto is_cs = [&](int i) -> bool { return (cs_bits[i >> 5] >> (i & 31)) & 1u; };
+      const int per = (n + T - 1) / T;
+      const int i0 = min(n, tid * per), i1 = min(n, i0 + per), cnt = i1 - i0;
+      unsigned off[kPer];
+      float ws[kPer];
+      unsigned heads = 0, cs_mask = 0;
+      unsigned prev = (cnt > 0 && i0 > 0) ? off_of(i0 - 1) : 0xffffffffu;
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) {
+        off[k] = 0u, ws[k] = 0.f;
+        if (k < cnt) {
+          off[k] = off_of(i0 + k);
+          ws[k] = __uint_as_float(ent[i0 + k].y);
+          const bool cs = is_cs(i0 + k);
+          if (cs || off[k] != prev) heads |= 1u << k;
+          if (cs) cs_mask |= 1u << k;
+          prev = off[k];
+        }
+      }
+      // running sums inside a run, left to right (point order) ...
+#pragma unroll
+      for (int k = 1; k < kPer; ++k)
+        if (k < cnt && !((heads >> k) & 1u)) ws[k] = ws[k - 1] + ws[k];
+      // ... and the run's total copied back to its head
+#pragma unroll
+      for (int k = kPer - 2; k >= 0; --k)
+        if (k + 1 < cnt && !((heads >> (k + 1)) & 1u)) ws[k] = ws[k + 1];
+      // the last run of the range may continue in the next threads' points
+      if (heads != 0u && i1 < n) {
+        const int last = 31 - __clz(heads);
+        float tot = 0.f;
+        unsigned o = 0u;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k)
+          if (k == last) tot = ws[k], o = off[k];
+        for (int i = i1; i < n && !is_cs(i) && off_of(i) == o; ++i) tot += __uint_as_float(ent[i].y);
+#pragma unroll
+        for (int k = 0; k < kPer; ++k)
+          if (k == last) ws[k] = tot;
+      }
+      // block-wide exclusive prefix of the head counts (every raw read above happens before its barrier)
+      const unsigned mine = __popc(heads);
+      unsigned incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) s_warp[warp] = incl;
+      __syncthreads();
+      unsigned base = incl - mine;
+      for (int w = 0; w < warp; ++w) base += s_warp[w];
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) {
+        if ((heads >> k) & 1u) {
+          const unsigned pos = base + __popc(heads & ((1u << k) - 1u));
+          ent[pos] = make_uint2(off[k], __float_as_uint(ws[k]));
+          if ((cs_mask >> k) & 1u) pos_map[i0 + k] = (unsigned short)pos;
+        }
+      }
+      if (tid == T - 1) pos_map[n] = (unsigned short)(base + mine);
+      __syncthreads();
+      if (tid < 32) {
+        const int lo = cell_lo[tid], hi = cell_hi[tid];
+        new_lo[tid] = pos_map[min(max(lo - cb, 0), n)];
+        new_hi[tid] = pos_map[min(max(hi - cb, 0), n)];
+      }
+    } else {
+      for (int i = tid; i < n; i += T) ent[i].x = off_of(i);
+      if (tid < 32) {
+        new_lo[tid] = min(max(cell_lo[tid] - cb, 0), n);
+        new_hi[tid] = min(max(cell_hi[tid] - cb, 0), n);
+      }
     }
     // ---- C: rounds ---------------------------------------------------------------------------------
-    const int a = max(my_lo, cb) - cb, e = min(my_hi, cb + n) - cb;
+    int a = 0, e = 0, cur = 0;
     for (int r = 0; r < n_rounds; ++r) {
       if (r + 1 < n_rounds) {
         stage_round(r + 1);
@@ -332,11 +450,14 @@ __global__ void __launch_bounds__(kL ? 32 * kL : 1024, kL ? (kL <= 10 ? 3 : (kL 
       } else {
         cp_async_wait<0>();
       }
-      __syncthreads();  // round r's rows (every thread's copies) and, for r == 0, the slot offsets
+      __syncthreads();  // round r's rows (every thread's copies) and, for r == 0, the entries and cell ranges
+      if (r == 0) a = cur = new_lo[cell], e = new_hi[cell];
       const unsigned char *bufp = rowbuf + (size_t)(r & 1) * half_bytes;
-      const unsigned rbase = (unsigned)r * half_bytes;
+      const unsigned rbase = (unsigned)r * half_bytes;  // offset of the round's first slot
       if (n_rounds == 1)
         rows_accumulate<FeatT, false>(ent, a, e, bufp, 0u, half_bytes, qoff0, qoff1, acc0, acc1);
+      else if (p.pixel_major)
+        rows_accumulate_cursor<FeatT>(ent, cur, e, bufp, rbase, half_bytes, qoff0, qoff1, acc0, acc1);
       else
         rows_accumulate<FeatT, true>(ent, a, e, bufp, rbase, half_bytes, qoff0, qoff1, acc0, acc1);
       __syncthreads();  // this half is refilled two rounds on; the chunk's tables are rebuilt after the last
@@ -416,6 +537,7 @@ int fwd_rows_launch(const rcb_pool_desc *d, const float *depth, const void *feat
   p.pitch = p.row_bytes + 16;
   // ~43 KB of row stage per CTA: 64 slots per half at C = 80 fp32
   p.sh = max(8, min(64, (int)(44032u / (2u * p.pitch))));
+  p.pixel_major = (d->flags & RCB_PLAN_PIXEL_MAJOR) ? 1 : 0;
   p.by_B = FastDiv::make((unsigned)p.B), p.by_tiles_x = FastDiv::make((unsigned)p.tiles_x);
   const long long grid = (long long)d->B * p.tiles_r * p.tiles_x;
   switch (d->feat_dtype) {

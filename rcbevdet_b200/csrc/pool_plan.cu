@@ -11,6 +11,8 @@
 //   STRUCTURED    ranks_depth unique, ranks_feat == pixel_of(ranks_depth) -> sort-free backward
 //   SAMPLE_LOCAL  the context row of every point lies in the sample of its BEV cell
 //                 (ranks_feat / rows-per-sample == ranks_bev / cells-per-sample) -> row-staging forward
+//   PIXEL_MAJOR   consecutive points of one cell never step back in ranks_feat (prepare's order)
+//                 -> the forward walks a cell with a cursor over its slot rounds
 #include "common.cuh"
 
 namespace rcb {
@@ -31,6 +33,7 @@ __global__ void __launch_bounds__(256)
       continue;
     }
     if (pix_per_sample <= 0 || rf / pix_per_sample != rb / cells_per_sample) bad_local |= RCB_PLAN_SAMPLE_LOCAL;
+    if (i > 0 && ranks_bev[i - 1] == rb && ranks_feat[i - 1] > rf) bad_local |= RCB_PLAN_PIXEL_MAJOR;
     if (D > 0 && HW > 0) {
       const int DHW = D * HW;
       const int bn = rd / DHW;

@@ -14,7 +14,7 @@ import ctypes
 import torch
 
 from . import _lib, bev_pool as _bp, plan as _plan
-from .prepare import prepare_async
+from .prepare import prepare_async, prepare_from_calib_async
 
 
 class _ViewPool(torch.autograd.Function):
@@ -86,4 +86,30 @@ def voxel_pooling_v2(coor, depth, feat, grid_lower_bound, grid_interval, grid_si
     bev = _ViewPool.apply(depth, feat, prepared)
     if collapse_z:
         bev = torch.cat(bev.unbind(dim=2), 1)                # view_transformer.py:203-204
+    return (bev, prepared) if return_prepared else bev
+
+
+def voxel_pooling_v2_from_calib(calib, axes, depth, feat, grid_lower_bound, grid_interval, grid_size,
+                                collapse_z=True, return_prepared=False):
+    """get_lidar_coor + voxel_pooling_v2 (view_transformer.py:290-294) as one device-side chain:
+    `calib` = (sensor2ego, ego2global, cam2imgs, post_rots, post_trans, bda) or a packed (cam, bda)
+    pair, `axes` = frustum_axes(...); depth (B,N,D,H,W); feat (B,N,C,H,W).  The frustum points
+    are generated inside the first prepare kernel; nothing of size P crosses PCIe or HBM as `coor`."""
+    C = int(feat.shape[2])
+    prepared = prepare_from_calib_async(calib, axes, grid_lower_bound, grid_interval, grid_size, device=depth.device)
+    if not fused_path_supports(C):
+        from .prepare import _finish
+        if return_prepared:
+            raise ValueError("return_prepared needs the fused path (C % 8 == 0, C <= 256)")
+        rb, rd, rf, st, ln = _finish(prepared)
+        gz, gy, gx = prepared.grid
+        if rb is None:
+            bev = torch.zeros((prepared.B, C, gz, gy, gx), dtype=torch.float32, device=depth.device)
+            bev = bev + 0.0 * (depth.sum() + feat.sum())
+        else:
+            bev = _bp.bev_pool_v2(depth, feat.permute(0, 1, 3, 4, 2), rd, rf, rb, (prepared.B, gz, gy, gx, C), st, ln)
+        return torch.cat(bev.unbind(dim=2), 1) if collapse_z else bev
+    bev = _ViewPool.apply(depth, feat.permute(0, 1, 3, 4, 2), prepared)
+    if collapse_z:
+        bev = torch.cat(bev.unbind(dim=2), 1)
     return (bev, prepared) if return_prepared else bev

@@ -1,0 +1,163 @@
+"""get_lidar_coor (view_transformer.py:115-157) fused into the prepare stage.
+
+The fused kernel generates every frustum point from the calibration in a FIXED, documented
+operation order (include/rcbevdet_b200.h, rcb_voxel_pooling_prepare_from_calib) -- the order of
+rcbevdet_b200.rig.lidar_coor.  Pinned three ways:
+  * the fused path and `prepare(rig.lidar_coor(calib))` agree on the BEV cell of EVERY frustum
+    point (point_cell, all P entries) and on all five outputs, bit for bit;
+  * on the golden cases that carry their calibration (rigA, augD), whose `coor` came from the
+    reference's own get_lidar_coor (batched matmul), the fused path reproduces the reference's ranks;
+  * the full-size R50 digest (reference code, config 1) is reproduced from the calibration alone.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+from rank_check import assert_same_ranks
+
+pytestmark = pytest.mark.gpu
+
+CALIB_KEYS = ("sensor2ego", "ego2global", "intrin", "post_rot", "post_tran", "bda")
+
+
+@pytest.mark.parametrize("B,input_size,grid_name,depth_cfg,aug", [
+    (2, (256, 704), "R50_GRID", None, None),            # BASELINE config 2 geometry
+    (3, (256, 704), "R50_GRID", None, 5),               # train-time image + BEV augmentation
+    (1, (900, 1600), "HIRES_GRID", None, None),         # BASELINE config 5 geometry
+    (2, (128, 352), "R50_GRID", (1.0, 60.0, 0.35), 11),  # D = 169 > 128: fewer pixels per tile
+])
+def test_fused_lidar_coor_matches_materialised_coor(B, input_size, grid_name, depth_cfg, aug):
+    import rcbevdet_b200 as rcb
+    from rcbevdet_b200 import rig
+    from rcbevdet_b200.prepare import prepare_async, prepare_from_calib_async
+    grid = getattr(rig, grid_name)
+    depth_cfg = list(depth_cfg or grid["depth"])
+    calib = rig.camera_rig(B, input_size=input_size, aug_seed=aug)
+    coor = rig.lidar_coor(calib, depth_cfg, input_size, 16)
+    lo, iv, sz = rig.grid_tensors(grid)
+    axes = rcb.frustum_axes(depth_cfg, input_size, 16)
+    a = prepare_async(coor.cuda(), lo, iv, sz)
+    b = prepare_from_calib_async(calib, axes, lo, iv, sz)
+    assert torch.equal(a.point_cell[:a.P], b.point_cell[:b.P]), "a frustum point changed its BEV cell"
+    assert torch.equal(a.counts, b.counts)
+    k, i = a.counts[:2].tolist()
+    assert k > 0
+    for name in ("ranks_bev", "ranks_depth", "ranks_feat"):
+        assert torch.equal(getattr(a, name)[:k], getattr(b, name)[:k]), name
+    for name in ("interval_starts", "interval_lengths"):
+        assert torch.equal(getattr(a, name)[:i], getattr(b, name)[:i]), name
+    assert torch.equal(a.cell_start, b.cell_start)
+    # and both agree with the CPU oracle on the materialised coor
+    want = oracle.voxel_pooling_prepare_v2_c(coor.numpy(), lo.numpy(), iv.numpy(), sz.numpy(), threads=8)
+    got = rcb.voxel_pooling_prepare_from_calib(calib, axes, lo, iv, sz)
+    assert_same_ranks(got, want)
+
+
+@pytest.mark.parametrize("name,depth_cfg,input_size", [("rigA", (1.0, 60.0, 5.0), (64, 176)),
+                                                       ("augD", (1.0, 60.0, 2.0), (128, 352))])
+def test_fused_lidar_coor_reproduces_reference_ranks(golden_prepare, name, depth_cfg, input_size):
+    """The golden `coor` is the output of the reference's get_lidar_coor (6-22 % of its floats differ
+    in the last bit from the fixed-order evaluation); the ranks must not."""
+    import rcbevdet_b200 as rcb
+    g = golden_prepare
+    calib = tuple(torch.from_numpy(g[f"{name}.{k}"]) for k in CALIB_KEYS)
+    fr = torch.from_numpy(g[f"{name}.frustum"])
+    axes = rcb.frustum_axes(frustum=fr)
+    assert all(torch.equal(x, y) for x, y in zip(axes, rcb.frustum_axes(list(depth_cfg), input_size, 16)))
+    lo, iv, sz = (torch.from_numpy(g[f"{name}.{k}"]) for k in ("lower", "interval", "size"))
+    rb, rd, rf, st, ln = (t.cpu().numpy() for t in rcb.voxel_pooling_prepare_from_calib(calib, axes, lo, iv, sz))
+    assert np.array_equal(rb, g[f"{name}.raw.ranks_bev"])
+    assert np.array_equal(st, g[f"{name}.raw.interval_starts"])
+    assert np.array_equal(ln, g[f"{name}.raw.interval_lengths"])
+    _, rd_c, rf_c = oracle.canonicalise(rb, rd, rf)
+    assert np.array_equal(rd_c, g[f"{name}.canon.ranks_depth"])
+    assert np.array_equal(rf_c, g[f"{name}.canon.ranks_feat"])
+
+
+def test_fused_lidar_coor_reproduces_full_size_reference_digest():
+    """tests/golden/prepare_full_digest.json: sha256 of the reference's outputs on config 1
+    (B=1 R50 rig, its own get_lidar_coor + voxel_pooling_prepare_v2) -- from the calibration alone."""
+    import rcbevdet_b200 as rcb
+    from rcbevdet_b200 import rig
+    GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with open(os.path.join(GOLDEN, "prepare_full_digest.json")) as f:
+        digest = json.load(f)
+    calib = rig.camera_rig(1)
+    axes = rcb.frustum_axes(rig.R50_GRID["depth"], rig.R50_INPUT, 16)
+    lo, iv, sz = rig.grid_tensors(rig.R50_GRID)
+    rb, rd, rf, st, ln = (t.cpu().numpy() for t in rcb.voxel_pooling_prepare_from_calib(calib, axes, lo, iv, sz))
+    assert (rb.shape[0], st.shape[0]) == (digest["K"], digest["I"])
+    rb_c, rd_c, rf_c = oracle.canonicalise(rb, rd, rf)
+    for name, arr in (("ranks_bev", rb_c), ("ranks_depth", rd_c), ("ranks_feat", rf_c),
+                      ("interval_starts", st), ("interval_lengths", ln)):
+        assert hashlib.sha256(arr.tobytes()).hexdigest() == digest["sha256"][name], name
+
+
+def test_fused_chain_from_calib_forward_backward():
+    """voxel_pooling_v2_from_calib == voxel_pooling_v2 on the materialised coor, bit for bit
+    (forward and both gradients), host-resident calibration."""
+    import rcbevdet_b200 as rcb
+    from rcbevdet_b200 import rig
+    B, C = 2, 80
+    grid = rig.R50_GRID
+    calib = rig.camera_rig(B, aug_seed=3)
+    coor = rig.lidar_coor(calib, grid["depth"], rig.R50_INPUT, 16)
+    _, N, D, H, W, _ = coor.shape
+    depth, feat = rig.pooling_inputs(B, N, D, H, W, C, seed=4)
+    lo, iv, sz = rig.grid_tensors(grid)
+    axes = rcb.frustum_axes(grid["depth"], rig.R50_INPUT, 16)
+    og = torch.randn(B, C, 128, 128, generator=torch.Generator().manual_seed(9)).cuda()
+    res = []
+    for fused in (False, True):
+        d = depth.cuda().requires_grad_(True)
+        f = feat.cuda().requires_grad_(True)
+        if fused:
+            bev = rcb.voxel_pooling_v2_from_calib(calib, axes, d, f, lo, iv, sz)
+        else:
+            bev = rcb.voxel_pooling_v2(coor.cuda(), d, f, lo, iv, sz)
+        bev.backward(og)
+        res.append((bev.detach(), d.grad, f.grad))
+    for x, y, what in zip(res[0], res[1], ("bev", "depth_grad", "feat_grad")):
+        assert torch.equal(x, y), what
+    assert float(res[0][0].abs().max()) > 0
+
+
+def test_install_fuses_view_transform_core():
+    """install(cls, fuse_lidar_coor=True): the non-accelerated branch of view_transform_core
+    (view_transformer.py:290-294) runs calibration -> BEV without materialising coor."""
+    import rcbevdet_b200 as rcb
+    from rcbevdet_b200 import rig
+
+    depth_cfg, input_size = [1.0, 60.0, 2.0], (128, 352)
+
+    class FakeVT:
+        accelerate = False
+        collapse_z = True
+        out_channels = 16
+
+        def __init__(self):
+            self.grid_lower_bound, self.grid_interval, self.grid_size = rig.grid_tensors(rig.R50_GRID)
+            self.frustum = rig.frustum(depth_cfg, input_size, 16)
+            self.D = self.frustum.shape[0]
+
+        def view_transform_core(self, input, depth, tran_feat):   # replaced by install()
+            raise AssertionError("reference branch must not run")
+
+    rcb.install(FakeVT, fuse_lidar_coor=True)
+    B = 1
+    calib = rig.camera_rig(B, input_size=input_size)
+    coor = rig.lidar_coor(calib, depth_cfg, input_size, 16)
+    _, N, D, H, W, _ = coor.shape
+    depth, feat = rig.pooling_inputs(B, N, D, H, W, 16, seed=6)
+    img = torch.zeros(B, N, 3, H, W)
+    inputs = [img.cuda()] + [t.cuda() for t in calib]
+    bev, dep = FakeVT().view_transform_core(inputs, depth.view(B * N, D, H, W).cuda(),
+                                            feat.view(B * N, 16, H, W).cuda())
+    lo, iv, sz = rig.grid_tensors(rig.R50_GRID)
+    want = rcb.voxel_pooling_v2(coor.cuda(), depth.cuda(), feat.cuda(), lo, iv, sz)
+    assert torch.equal(bev, want)

@@ -17,6 +17,7 @@ import pytest
 import torch
 
 from oracle import oracle, ref_cuda
+from rank_check import assert_same_ranks
 
 pytestmark = pytest.mark.gpu
 
@@ -30,21 +31,8 @@ def _close(got, want, rtol, what):
     assert err <= rtol * scale, f"{what}: max abs err {err:.3e} > {rtol} * {scale:.3e}"
 
 
-def _canon(t3):
-    rb, rd, rf = (np.asarray(t.cpu().numpy() if isinstance(t, torch.Tensor) else t) for t in t3)
-    return oracle.canonicalise(rb, rd, rf)
-
-
 def _check_ranks(got, want):
-    """ranks_bev / interval arrays bit-exact as they come; ranks_depth / ranks_feat bit-exact after
-    the canonical tie order (the reference's argsort leaves ties unspecified)."""
-    g = [t.cpu().numpy() for t in got]
-    assert np.array_equal(g[0], want[0]), "ranks_bev"
-    assert np.array_equal(g[3], want[3]), "interval_starts"
-    assert np.array_equal(g[4], want[4]), "interval_lengths"
-    cg, cw = oracle.canonicalise(g[0], g[1], g[2]), oracle.canonicalise(want[0], want[1], want[2])
-    assert np.array_equal(cg[1], cw[1]), "ranks_depth"
-    assert np.array_equal(cg[2], cw[2]), "ranks_feat"
+    assert_same_ranks(got, want)
 
 
 def test_config2_full_batch_fwd_bwd():

@@ -5,6 +5,7 @@ import pytest
 import torch
 
 from oracle import oracle
+from rank_check import assert_same_ranks
 
 pytestmark = pytest.mark.gpu
 
@@ -67,8 +68,7 @@ def test_prepare_then_pool_forward_backward(aug):
     ranks, shape, feat_rows, want = _oracle_pool(coor, depth, feat, grid)
     lo, iv, sz = rig.grid_tensors(grid)
     g_ranks = rcb.voxel_pooling_prepare_v2(coor.cuda(), lo, iv, sz)
-    for g, w in zip(g_ranks, ranks):
-        assert np.array_equal(g.cpu().numpy(), w)
+    assert_same_ranks(g_ranks, ranks)
     rb, rd, rf, st, ln = g_ranks
     d = depth.cuda().requires_grad_(True)
     f = feat.cuda().requires_grad_(True)
@@ -318,8 +318,7 @@ def test_hires_full_size_properties():
     lo, iv, sz = rig.grid_tensors(grid)
     got = rcb.voxel_pooling_prepare_v2(coor.cuda(), lo, iv, sz)
     want = oracle.voxel_pooling_prepare_v2_c(coor.numpy(), lo.numpy(), iv.numpy(), sz.numpy(), threads=8)
-    for g, w in zip(got, want):
-        assert np.array_equal(g.cpu().numpy(), w)
+    assert_same_ranks(got, want)
     rb, rd, rf, st, ln = got
     assert int(ln.max()) > 512                      # exercises the CTA sort tier on real geometry
     assert bool((rb[1:] >= rb[:-1]).all())
