@@ -46,9 +46,7 @@ typedef struct CUstream_st *rcb_stream_t; /* == cudaStream_t */
 #define RCB_PLAN_INTERVALS_OK 2   /* intervals tile [0, n_points) contiguously, lengths > 0           */
 #define RCB_PLAN_SORTED_CELLS 4   /* interval cells strictly increasing -> zero-filling tile kernel    */
 #define RCB_PLAN_STRUCTURED 8     /* ranks_depth unique and ranks_feat == pixel_of(ranks_depth)        */
-#define RCB_PLAN_SAMPLE_LOCAL 16  /* ranks_feat[i] lies in the sample of ranks_bev[i] -> row-staging forward */
-#define RCB_PLAN_PIXEL_MAJOR 32   /* inside a cell ranks_feat never decreases -> cursor walk, merged depth bins      */
-#define RCB_PLAN_ALL 63
+#define RCB_PLAN_ALL 15
 
 int rcb_version(void);
 const char *rcb_error_string(int code);
@@ -160,15 +158,18 @@ int rcb_pool_build_cellmap(const rcb_pool_desc *d, const int *ranks_bev, const i
  * Forward.  depth: float32 [n_depth]; feat: [n_pixels, C] channels last, `feat_dtype`;
  * out: float32 [B*Z*Y*X*C] in `layout`, fully written on return (the reference needs it
  * pre-zeroed, bev_pool.py:27, and a permute copy afterwards, bev_pool.py:91 -- neither here).
- *   cell_start != NULL (ranks with RCB_PLAN_SORTED_CELLS): tile kernel, one pass.
+ *   cell_start != NULL (ranks with RCB_PLAN_SORTED_CELLS): cell-stationary kernels.  They need
+ *     workspace >= rcb_pool_fwd_workspace_bytes() (8 bytes per point: merged (row, weight) entries).
  *   cell_start == NULL: general path for arbitrary ranks (memset + one warp per interval).
  * Argument order of the rank arrays follows bev_pool_v2_forward (bev_pool.cpp:30-38):
  * interval_lengths BEFORE interval_starts.
  */
+size_t rcb_pool_fwd_workspace_bytes(const rcb_pool_desc *d);
 int rcb_bev_pool_v2_fwd(const rcb_pool_desc *d, const float *depth, const void *feat,
                         const int *ranks_depth, const int *ranks_feat, const int *ranks_bev,
                         const int *interval_lengths, const int *interval_starts,
-                        const int *cell_start, float *out, int device, rcb_stream_t stream);
+                        const int *cell_start, float *out, void *workspace, size_t workspace_bytes,
+                        int device, rcb_stream_t stream);
 
 /*
  * Backward (bev_pool.cpp:74-104).  out_grad float32 in `layout`; depth_grad float32 [n_depth];

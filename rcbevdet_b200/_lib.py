@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("RCB_LIB_PATH") or os.path.join(_PKG, "lib", "librcbev
 RCB_OK = 0
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 LAYOUT_CELLS_C, LAYOUT_B_C_CELLS = 0, 1
-PLAN_RANGES_OK, PLAN_INTERVALS_OK, PLAN_SORTED_CELLS, PLAN_STRUCTURED, PLAN_SAMPLE_LOCAL, PLAN_PIXEL_MAJOR, PLAN_ALL = 1, 2, 4, 8, 16, 32, 63
+PLAN_RANGES_OK, PLAN_INTERVALS_OK, PLAN_SORTED_CELLS, PLAN_STRUCTURED, PLAN_ALL = 1, 2, 4, 8, 15
 
 
 class PrepareDesc(ctypes.Structure):
@@ -54,7 +54,8 @@ SIGNATURES = {
     "rcb_pool_validate_workspace_bytes": (_sz, [ctypes.POINTER(PoolDesc)]),
     "rcb_pool_validate": (_i, [ctypes.POINTER(PoolDesc)] + [_vp] * 7 + [_vp, _sz, _i, _vp]),
     "rcb_pool_build_cellmap": (_i, [ctypes.POINTER(PoolDesc), _vp, _vp, _vp, _i, _vp]),
-    "rcb_bev_pool_v2_fwd": (_i, [ctypes.POINTER(PoolDesc)] + [_vp] * 9 + [_i, _vp]),
+    "rcb_pool_fwd_workspace_bytes": (_sz, [ctypes.POINTER(PoolDesc)]),
+    "rcb_bev_pool_v2_fwd": (_i, [ctypes.POINTER(PoolDesc)] + [_vp] * 9 + [_vp, _sz, _i, _vp]),
     "rcb_pool_bwd_workspace_bytes": (_sz, [ctypes.POINTER(PoolDesc)]),
     "rcb_bev_pool_v2_bwd": (_i, [ctypes.POINTER(PoolDesc)] + [_vp] * 9 + [_vp, _sz, _i, _vp]),
     "rcb_planes_to_rows": (_i, [_vp, _vp, _i, _i, _i, _ll, _i, _i, _vp]),

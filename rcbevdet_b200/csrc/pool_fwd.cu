@@ -389,12 +389,14 @@ static int launch_intervals(const rcb_pool_desc *d, const float *depth, const vo
   return RCB_OK;
 }
 
-bool fwd_rows_eligible(const rcb_pool_desc *d, const void *feat, const int *cell_start);
-int fwd_rows_launch(const rcb_pool_desc *d, const float *depth, const void *feat, const int *ranks_depth,
-                    const int *ranks_feat, const int *cell_start, float *out, cudaStream_t s);
+bool fwd_cells_eligible(const rcb_pool_desc *d, const void *feat, const int *cell_start);
+size_t fwd_cells_workspace_bytes(const rcb_pool_desc *d);
+int fwd_cells_launch(const rcb_pool_desc *d, const float *depth, const void *feat, const int *ranks_depth,
+                     const int *ranks_feat, const int *ranks_bev, const int *cell_start, float *out,
+                     void *workspace, size_t workspace_bytes, int sms, cudaStream_t s);
 
-// Diagnostic knob (A/B timing only): RCB_FWD_KERNEL=tile keeps round 1's L1-gather kernel.
-static bool fwd_rows_disabled() {
+// Diagnostic knob (A/B timing only): RCB_FWD_KERNEL=tile keeps round 1's lane-group kernel.
+static bool fwd_cells_disabled() {
   static const bool off = [] {
     const char *v = getenv("RCB_FWD_KERNEL");
     return v != nullptr && v[0] == 't';
@@ -418,11 +420,17 @@ int check_pool_desc(const rcb_pool_desc *d) {
 
 using namespace rcb;
 
+extern "C" size_t rcb_pool_fwd_workspace_bytes(const rcb_pool_desc *d) {
+  if (check_pool_desc(d) != RCB_OK) return 0;
+  return fwd_cells_workspace_bytes(d);
+}
+
 extern "C" int rcb_bev_pool_v2_fwd(const rcb_pool_desc *d, const float *depth, const void *feat,
                                    const int *ranks_depth, const int *ranks_feat,
                                    const int *ranks_bev, const int *interval_lengths,
                                    const int *interval_starts, const int *cell_start, float *out,
-                                   int device, rcb_stream_t stream) {
+                                   void *workspace, size_t workspace_bytes, int device,
+                                   rcb_stream_t stream) {
   int rc = check_pool_desc(d);
   if (rc != RCB_OK) return rc;
   if (!out) return RCB_ERR_ARG;
@@ -432,9 +440,10 @@ extern "C" int rcb_bev_pool_v2_fwd(const rcb_pool_desc *d, const float *depth, c
   const int cps = d->Z * d->Y * d->X;
   const size_t out_bytes = (size_t)d->B * cps * d->C * 4;
 
-  if (!fwd_rows_disabled() && fwd_rows_eligible(d, feat, cell_start)) {
-    if (d->n_points > 0 && (!depth || !feat || !ranks_depth || !ranks_feat)) return RCB_ERR_ARG;
-    return fwd_rows_launch(d, depth, feat, ranks_depth, ranks_feat, cell_start, out, s);
+  if (!fwd_cells_disabled() && fwd_cells_eligible(d, feat, cell_start)) {
+    if (d->n_points > 0 && (!depth || !feat || !ranks_depth || !ranks_feat || !ranks_bev)) return RCB_ERR_ARG;
+    return fwd_cells_launch(d, depth, feat, ranks_depth, ranks_feat, ranks_bev, cell_start, out, workspace,
+                            workspace_bytes, sm_count_cached(device), s);
   }
   const int elem = d->feat_dtype == RCB_DTYPE_F32 ? 4 : 2;
   const bool tile_ok = cell_start != nullptr && (d->C % 8) == 0 && d->C <= 256 && (long long)d->n_pixels * d->C * elem < (1ll << 32) &&

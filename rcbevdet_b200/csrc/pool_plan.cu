@@ -9,17 +9,12 @@
 //                 an interval carries the interval's cell in ranks_bev
 //   SORTED_CELLS  interval cells strictly increasing  -> dense CSR `cell_start`, tile kernel
 //   STRUCTURED    ranks_depth unique, ranks_feat == pixel_of(ranks_depth) -> sort-free backward
-//   SAMPLE_LOCAL  the context row of every point lies in the sample of its BEV cell
-//                 (ranks_feat / rows-per-sample == ranks_bev / cells-per-sample) -> row-staging forward
-//   PIXEL_MAJOR   consecutive points of one cell never step back in ranks_feat (prepare's order)
-//                 -> the forward walks a cell with a cursor over its slot rounds
 #include "common.cuh"
 
 namespace rcb {
 
 __global__ void __launch_bounds__(256)
-    k_validate_points(int n_points, int n_depth, int n_pixels, int n_cells, int D, int HW, int pix_per_sample,
-                      int cells_per_sample,
+    k_validate_points(int n_points, int n_depth, int n_pixels, int n_cells, int D, int HW,
                       const int *__restrict__ ranks_depth, const int *__restrict__ ranks_feat,
                       const int *__restrict__ ranks_bev, int *__restrict__ point_cell,
                       int *__restrict__ bad) {
@@ -29,11 +24,9 @@ __global__ void __launch_bounds__(256)
     const int rd = ranks_depth[i], rf = ranks_feat[i], rb = ranks_bev[i];
     const bool in_range = rd >= 0 && rd < n_depth && rf >= 0 && rf < n_pixels && rb >= 0 && rb < n_cells;
     if (!in_range) {
-      bad_local |= RCB_PLAN_RANGES_OK | RCB_PLAN_STRUCTURED | RCB_PLAN_SAMPLE_LOCAL;
+      bad_local |= RCB_PLAN_RANGES_OK | RCB_PLAN_STRUCTURED;
       continue;
     }
-    if (pix_per_sample <= 0 || rf / pix_per_sample != rb / cells_per_sample) bad_local |= RCB_PLAN_SAMPLE_LOCAL;
-    if (i > 0 && ranks_bev[i - 1] == rb && ranks_feat[i - 1] > rf) bad_local |= RCB_PLAN_PIXEL_MAJOR;
     if (D > 0 && HW > 0) {
       const int DHW = D * HW;
       const int bn = rd / DHW;
@@ -132,8 +125,7 @@ extern "C" int rcb_pool_validate(const rcb_pool_desc *d, const int *ranks_depth,
   RCB_CUDA_TRY(cudaMemsetAsync(point_cell, 0xff, (size_t)d->n_depth * 4, s));
   if (d->n_points > 0) {
     k_validate_points<<<min(ceil_div(d->n_points, 256), sms * 16), 256, 0, s>>>(
-        d->n_points, d->n_depth, d->n_pixels, n_cells, d->D, d->HW,
-        (d->n_pixels > 0 && d->n_pixels % d->B == 0) ? d->n_pixels / d->B : 0, n_cells / d->B, ranks_depth, ranks_feat, ranks_bev,
+        d->n_points, d->n_depth, d->n_pixels, n_cells, d->D, d->HW, ranks_depth, ranks_feat, ranks_bev,
         point_cell, bad);
     RCB_LAUNCH_CHECK();
   }

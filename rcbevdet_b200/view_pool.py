@@ -34,11 +34,8 @@ class _ViewPool(torch.autograd.Function):
         if d.n_depth != prepared.P or d.n_pixels * d.D != d.n_depth:
             raise ValueError("depth / feat shapes do not match the frustum that `coor` describes")
         out = torch.empty((prepared.B, C, gz, gy, gx), dtype=torch.float32, device=dev)
-        _lib.check(_lib.lib().rcb_bev_pool_v2_fwd(
-            ctypes.byref(d), _lib.ptr(depth_c), _lib.ptr(rows), _lib.ptr(prepared.ranks_depth),
-            _lib.ptr(prepared.ranks_feat), _lib.ptr(prepared.ranks_bev), None, None,
-            _lib.ptr(prepared.cell_start), _lib.ptr(out), dev.index, _lib.stream_ptr(dev)),
-            "rcb_bev_pool_v2_fwd")
+        _bp.pool_forward(d, depth_c, rows, prepared.ranks_depth, prepared.ranks_feat, prepared.ranks_bev, None, None,
+                         prepared.cell_start, out)
         ctx.save_for_backward(depth_c, rows, prepared.ranks_depth, prepared.ranks_feat, prepared.ranks_bev)
         plan = _plan.PoolPlan(_lib.PLAN_ALL, prepared.cell_start, prepared.point_cell, prepared.D,
                               prepared.HW, prepared.n_cells, prepared.P)
@@ -54,10 +51,11 @@ class _ViewPool(torch.autograd.Function):
 
 
 def fused_path_supports(C):
-    """The sync-free chain drives the CSR (cell-stationary) forward kernel, which owns whole
-    128-bit channel quads: C % 8 == 0 and C <= 256.  Any other channel count (the reference
-    accepts every C) takes the two-call route below, which reads the counts back once."""
-    return C % 8 == 0 and 0 < C <= 256
+    """The sync-free chain drives the CSR (cell-stationary) forward kernels, which own whole
+    128-bit channel quads: C % 4 == 0 up to 128 channels, C % 8 == 0 up to 256.  Any other channel
+    count (the reference accepts every C) takes the two-call route below, which reads the counts
+    back once."""
+    return 0 < C <= 256 and C % 4 == 0 and (C <= 128 or C % 8 == 0)
 
 
 def voxel_pooling_v2(coor, depth, feat, grid_lower_bound, grid_interval, grid_size, collapse_z=True,
@@ -70,7 +68,7 @@ def voxel_pooling_v2(coor, depth, feat, grid_lower_bound, grid_interval, grid_si
         # through its general kernels, with the real n_kept / n_intervals
         from .prepare import voxel_pooling_prepare_v2
         if return_prepared:
-            raise ValueError("return_prepared needs the fused path (C % 8 == 0, C <= 256)")
+            raise ValueError("return_prepared needs the fused path (see fused_path_supports)")
         rb, rd, rf, st, ln = voxel_pooling_prepare_v2(coor, grid_lower_bound, grid_interval, grid_size)
         B = int(coor.shape[0])
         gx, gy, gz = (int(float(v)) for v in (grid_size.tolist() if isinstance(grid_size, torch.Tensor)
@@ -100,7 +98,7 @@ def voxel_pooling_v2_from_calib(calib, axes, depth, feat, grid_lower_bound, grid
     if not fused_path_supports(C):
         from .prepare import _finish
         if return_prepared:
-            raise ValueError("return_prepared needs the fused path (C % 8 == 0, C <= 256)")
+            raise ValueError("return_prepared needs the fused path (see fused_path_supports)")
         rb, rd, rf, st, ln = _finish(prepared)
         gz, gy, gx = prepared.grid
         if rb is None:

@@ -331,5 +331,8 @@ def test_hires_full_size_properties():
     o2 = rcb.bev_pool_v2(2.0 * d, fv, rd, rf, rb, shape, st, ln)
     assert torch.allclose(o2, 2.0 * o1, rtol=1e-6, atol=0)
     rows = fv.reshape(-1, 16).double()
-    total = (d.flatten()[rd.long()].double()[:, None] * rows[rf.long()]).sum(0)
-    assert torch.allclose(o1.double().sum(dim=(0, 2, 3, 4)), total, rtol=1e-6)
+    terms = d.flatten()[rd.long()].double()[:, None] * rows[rf.long()]
+    total, scale = terms.sum(0), terms.abs().sum(0)
+    # fp32 accumulation inside a cell: the error is relative to the sum of magnitudes, not to the
+    # (heavily cancelling) signed total
+    assert bool(((o1.double().sum(dim=(0, 2, 3, 4)) - total).abs() <= 1e-6 * scale).all())
