@@ -158,18 +158,16 @@ int rcb_pool_build_cellmap(const rcb_pool_desc *d, const int *ranks_bev, const i
  * Forward.  depth: float32 [n_depth]; feat: [n_pixels, C] channels last, `feat_dtype`;
  * out: float32 [B*Z*Y*X*C] in `layout`, fully written on return (the reference needs it
  * pre-zeroed, bev_pool.py:27, and a permute copy afterwards, bev_pool.py:91 -- neither here).
- *   cell_start != NULL (ranks with RCB_PLAN_SORTED_CELLS): cell-stationary kernels.  They need
- *     workspace >= rcb_pool_fwd_workspace_bytes() (8 bytes per point: merged (row, weight) entries).
+ *   cell_start != NULL (ranks with RCB_PLAN_SORTED_CELLS): cell-stationary kernel (one warp pools a
+ *     cell; C % 4 == 0 up to 128 channels, C % 8 == 0 up to 256).
  *   cell_start == NULL: general path for arbitrary ranks (memset + one warp per interval).
  * Argument order of the rank arrays follows bev_pool_v2_forward (bev_pool.cpp:30-38):
  * interval_lengths BEFORE interval_starts.
  */
-size_t rcb_pool_fwd_workspace_bytes(const rcb_pool_desc *d);
 int rcb_bev_pool_v2_fwd(const rcb_pool_desc *d, const float *depth, const void *feat,
                         const int *ranks_depth, const int *ranks_feat, const int *ranks_bev,
                         const int *interval_lengths, const int *interval_starts,
-                        const int *cell_start, float *out, void *workspace, size_t workspace_bytes,
-                        int device, rcb_stream_t stream);
+                        const int *cell_start, float *out, int device, rcb_stream_t stream);
 
 /*
  * Backward (bev_pool.cpp:74-104).  out_grad float32 in `layout`; depth_grad float32 [n_depth];

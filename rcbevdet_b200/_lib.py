@@ -54,8 +54,7 @@ SIGNATURES = {
     "rcb_pool_validate_workspace_bytes": (_sz, [ctypes.POINTER(PoolDesc)]),
     "rcb_pool_validate": (_i, [ctypes.POINTER(PoolDesc)] + [_vp] * 7 + [_vp, _sz, _i, _vp]),
     "rcb_pool_build_cellmap": (_i, [ctypes.POINTER(PoolDesc), _vp, _vp, _vp, _i, _vp]),
-    "rcb_pool_fwd_workspace_bytes": (_sz, [ctypes.POINTER(PoolDesc)]),
-    "rcb_bev_pool_v2_fwd": (_i, [ctypes.POINTER(PoolDesc)] + [_vp] * 9 + [_vp, _sz, _i, _vp]),
+    "rcb_bev_pool_v2_fwd": (_i, [ctypes.POINTER(PoolDesc)] + [_vp] * 9 + [_i, _vp]),
     "rcb_pool_bwd_workspace_bytes": (_sz, [ctypes.POINTER(PoolDesc)]),
     "rcb_bev_pool_v2_bwd": (_i, [ctypes.POINTER(PoolDesc)] + [_vp] * 9 + [_vp, _sz, _i, _vp]),
     "rcb_planes_to_rows": (_i, [_vp, _vp, _i, _i, _i, _ll, _i, _i, _vp]),

@@ -74,16 +74,12 @@ def _pool_desc(depth, rows, ranks_depth, interval_lengths, bev_feat_shape, layou
 
 def pool_forward(desc, depth, rows, ranks_depth, ranks_feat, ranks_bev, interval_lengths, interval_starts,
                  cell_start, out):
-    """rcb_bev_pool_v2_fwd with its workspace (8 bytes per point: the merged (row, weight) entries of
-    the cell-stationary kernels) allocated from torch's caching allocator."""
-    lib = _lib.lib()
+    """rcb_bev_pool_v2_fwd on the caller's current stream."""
     dev = out.device
-    ws_bytes = lib.rcb_pool_fwd_workspace_bytes(ctypes.byref(desc)) if cell_start is not None else 0
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
-    _lib.check(lib.rcb_bev_pool_v2_fwd(
+    _lib.check(_lib.lib().rcb_bev_pool_v2_fwd(
         ctypes.byref(desc), _lib.ptr(depth), _lib.ptr(rows), _lib.ptr(ranks_depth), _lib.ptr(ranks_feat),
         _lib.ptr(ranks_bev), _lib.ptr(interval_lengths), _lib.ptr(interval_starts), _lib.ptr(cell_start),
-        _lib.ptr(out), _lib.ptr(ws), ws_bytes, dev.index, _lib.stream_ptr(dev)), "rcb_bev_pool_v2_fwd")
+        _lib.ptr(out), dev.index, _lib.stream_ptr(dev)), "rcb_bev_pool_v2_fwd")
 
 
 def _forward(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, interval_starts,

@@ -1,61 +1,61 @@
-// Row F -- bev_pool_v2 forward, cell-stationary kernel pair (the product path for ranks whose cells
-// are sorted, i.e. everything prepare emits and everything rcb_pool_validate proves sorted).
+// Row F -- bev_pool_v2 forward, cell-stationary kernel (the product path for ranks whose cells are
+// sorted, i.e. everything prepare emits and everything rcb_pool_validate proves sorted).
 // Reference: mmdet3d/ops/bev_pool_v2/src/bev_pool_cuda.cu:21-48; the zero-fill and the permute copy of
 // mmdet3d/ops/bev_pool_v2/bev_pool.py:27,91 are folded in (every cell written once, final layout).
 //
-//   k_fwd_entries  one thread per sorted point: (context-row byte offset, depth weight) pairs, 8 bytes
-//                  each, in sorted order.  Consecutive points of one cell that read the SAME row -- the
-//                  depth bins of one (cell, pixel) pair, adjacent in prepare's (pixel, depth) order,
-//                  1.42 per pair on the R50 grid -- are merged here: the first carries the sum of their
-//                  depth weights (added in point order), the others are marked "skip".  This is also
-//                  where the depth gather happens, with one independent load per thread instead of a
-//                  dependent one inside the pooling loop.
-//   k_fwd_cells    one CTA per 8 x 4 patch of BEV cells, thread <-> (cell, 128-bit channel quad).
-//                  A thread walks the entries of ITS cell straight from global memory (broadcast
-//                  128-bit loads of two entries, L1-resident lines), loads its quad of every
-//                  non-skipped row through L1 -- the patch shape makes neighbouring cells, which see
-//                  the same pixels along a ray, share rows there -- and accumulates in registers.  No
-//                  shared-memory staging, no partial sums, no barrier before the write-out; the patch
-//                  leaves through a shared-memory transpose as (B, C, Z*Y*X) runs of 8 cells per
-//                  channel row, or directly as channels-last rows.  Empty cells get their zeros here.
+// k_fwd_cells: one CTA per kPatchX x kPatchY patch of BEV cells; a WARP pools one cell at a time.
+// The patch's cells are ranked by length and dealt to the warps in snake order (longest first, a
+// static LPT schedule: no queue, no atomics).  Between the opening barrier (cell bounds + order)
+// and the closing one (write-out) the warps never wait for each other: the kernel's critical path
+// is one cell (<= 656 points on the R50 grid), not one patch (6 k points).
 //
-// The order of additions inside a cell is the point order (runs folded first): bit-reproducible.
+// A warp's cells are cut into chunks of 32 points and run through a three-stage software pipeline,
+// lane <-> point: (1) coalesced loads of ranks_feat / ranks_depth of chunk t + 2, (2) the depth
+// gather of chunk t + 1, (3) chunk t: the depth bins of one (cell, pixel) pair -- adjacent in
+// prepare's (pixel, depth) order, 1.42 per pair on the R50 grid -- are merged in registers (groups
+// of <= 4, weights summed in point order) and the surviving (row, weight) entries are compacted
+// into the warp's 256 bytes of shared memory.  Then lane <-> 128-bit channel quad: every entry
+// costs half a broadcast LDS.128, one IMAD.WIDE, one LDG.128 of the context row through L1 -- the
+// 2-D patch makes neighbouring cells, which see the same pixels along a ray, share rows there --
+// and two packed FMAs; kRows rows are in flight per warp.  No partial sums, no atomics: the order
+// of additions inside a cell is the point order (groups folded first), bit-reproducible.
+//
+// The patch leaves through a shared-memory transpose as (B, C, Z*Y*X) runs of kPatchX cells per
+// channel row, or directly as channels-last rows.  Empty cells get their zeros here.
 #include "common.cuh"
 
 namespace rcb {
 
-constexpr int kCellsTileX = 8;
-constexpr int kCellsTileY = 4;
-constexpr unsigned kSkipEntry = 0xffffffffu;
-
-struct FwdEntriesParams {
-  const float *depth;
-  const int *ranks_depth, *ranks_feat, *ranks_bev;
-  const int *n_ptr;  // number of valid points (cell_start[n_cells]) -- a device value in the fused chain
-  uint2 *entries;
-  unsigned row_bytes;
-};
-
-__global__ void __launch_bounds__(256) k_fwd_entries(FwdEntriesParams p) {
-  pdl_prologue();
-  const int n = __ldg(p.n_ptr);
-  const int stride = gridDim.x * blockDim.x;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int rb = __ldg(p.ranks_bev + i), rf = __ldg(p.ranks_feat + i);
-    if (i > 0 && __ldg(p.ranks_bev + i - 1) == rb && __ldg(p.ranks_feat + i - 1) == rf) {
-      p.entries[i] = make_uint2(kSkipEntry, 0u);
-      continue;
-    }
-    float w = ld_stream_f32(p.depth + __ldg(p.ranks_depth + i));
-    for (int j = i + 1; j < n && __ldg(p.ranks_bev + j) == rb && __ldg(p.ranks_feat + j) == rf; ++j)
-      w += ld_stream_f32(p.depth + __ldg(p.ranks_depth + j));
-    p.entries[i] = make_uint2((unsigned)rf * p.row_bytes, __float_as_uint(w));
-  }
-}
+#ifndef RCB_FWD_PX
+#define RCB_FWD_PX 8
+#endif
+#ifndef RCB_FWD_PY
+#define RCB_FWD_PY 4
+#endif
+#ifndef RCB_FWD_WARPS
+#define RCB_FWD_WARPS 8
+#endif
+#ifndef RCB_FWD_ROWS
+#define RCB_FWD_ROWS 4  // context rows in flight per warp
+#endif
+#ifndef RCB_FWD_CTAS
+#define RCB_FWD_CTAS 5  // CTAs per SM the register budget is cut for
+#endif
+constexpr int kPatchX = RCB_FWD_PX;
+constexpr int kPatchY = RCB_FWD_PY;
+constexpr int kPatchCells = kPatchX * kPatchY;
+constexpr int kFwdWarps = RCB_FWD_WARPS;
+constexpr int kCellWarps = kPatchCells / 32;           // warps that do the bookkeeping, lane <-> cell
+constexpr int kFwdRounds = kPatchCells / kFwdWarps;    // cells per warp
+constexpr int kTilePitch = kPatchCells + 1;
+constexpr int kRowsInFlight = RCB_FWD_ROWS;
+static_assert(kPatchCells % 32 == 0 && kPatchCells % kFwdWarps == 0 && kCellWarps <= kFwdWarps, "patch shape");
+static_assert((kPatchX & (kPatchX - 1)) == 0, "kPatchX is a power of two");
 
 struct FwdCellsParams {
+  const float *depth;
   const void *feat;
-  const uint2 *entries;
+  const int *ranks_depth, *ranks_feat;
   const int *cell_start;
   float *out;
   int C;
@@ -64,6 +64,7 @@ struct FwdCellsParams {
   int cells_per_sample;
   int layout;
   int B;
+  unsigned row_bytes;
   FastDiv by_B, by_tiles_x;
 };
 
@@ -84,119 +85,277 @@ __device__ __forceinline__ void cells_fma(float4 &acc, const float4 v, const flo
   acc = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
-// kQ channel quads per lane (quad j of lane l = l + j * kLanes); kLanes lanes per cell
-// (C = 4 * kQ * kLanes), kLanes == 0: run time.  blockDim.x == 32 * lanes.
+// one chunk (<= 32 consecutive points of one cell) on its way through the pipeline
+struct FwdChunk {
+  int n;      // valid points, -1: no chunk
+  int cell;   // patch-local cell
+  int last;   // the cell ends with this chunk
+  int rf;     // lane's ranks_feat
+  int rd;     // lane's ranks_depth
+  float w;    // lane's depth weight
+};
+
+// kQ channel quads per lane (quad j of lane l = l + j * lanes); kLanes lanes carry a row
+// (C = 4 * kQ * lanes), kLanes == 0: run time.
 template <typename FeatT, int kLanes, int kQ>
-__global__ void __launch_bounds__(kLanes ? 32 * kLanes : 1024, kLanes ? (kLanes <= 20 ? 2 : 1) : 1)
-    k_fwd_cells(FwdCellsParams p) {
+__global__ void __launch_bounds__(32 * kFwdWarps, RCB_FWD_CTAS) k_fwd_cells(FwdCellsParams p) {
   pdl_prologue();
-  extern __shared__ __align__(16) float cells_ts[];  // [C][33] write-out tile (B_C_CELLS layout only)
+  extern __shared__ __align__(16) float cells_ts[];  // [C][kTilePitch] write-out tile (B_C_CELLS layout only)
+  __shared__ __align__(16) uint2 s_ent[kFwdWarps][32];
+  __shared__ int s_lo[kPatchCells], s_hi[kPatchCells];
+  __shared__ unsigned char s_order[kPatchCells];
+#ifndef RCB_FWD_STATIC
+  __shared__ int s_next;
+  if (threadIdx.x == 0) s_next = 0;
+#endif
+  constexpr int kRows = kRowsInFlight / kQ;  // per warp, whatever the quads per lane
   const int lanes = kLanes ? kLanes : p.C / (4 * kQ);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool to_tile = p.layout == RCB_LAYOUT_B_C_CELLS;
   // Launch order: patches nearest the grid centre first, samples interleaved (point density peaks
-  // around the ego vehicle, so the long cells start at once).  Any order is correct.
+  // around the ego vehicle, so the heavy patches start at once).  Any order is correct.
   const int t = (int)p.by_B.div(blockIdx.x);
   const int b = (int)blockIdx.x - t * p.B;
   const int t_r = (int)p.by_tiles_x.div((unsigned)t);
-  const int x0 = cells_zigzag(t - t_r * p.tiles_x, p.tiles_x) * kCellsTileX;
-  const int r0 = cells_zigzag(t_r, p.tiles_r) * kCellsTileY;
-  const int nx = min(kCellsTileX, p.X - x0), nr = min(kCellsTileY, p.R - r0);
+  const int x0 = cells_zigzag(t - t_r * p.tiles_x, p.tiles_x) * kPatchX;
+  const int r0 = cells_zigzag(t_r, p.tiles_r) * kPatchY;
+  const int nx = min(kPatchX, p.X - x0), nr = min(kPatchY, p.R - r0);
   const int cell_base = b * p.cells_per_sample;
 
-  const int cell = tid / lanes, l = tid - cell * lanes;
-  const int cty = cell / kCellsTileX, ctx = cell % kCellsTileX;
-  const bool cell_ok = cty < nr && ctx < nx;
-  const int gcell = cell_base + (r0 + cty) * p.X + x0 + ctx;
-  int s = 0, e = 0;
-  if (cell_ok) {
-    s = __ldg(p.cell_start + gcell);
-    e = __ldg(p.cell_start + gcell + 1);
+  if (warp < kCellWarps) {
+    // lane <-> cell: every bookkeeping warp reads all bounds (its own cells' rank needs all lengths)
+    int len[kCellWarps], lo_mine = 0;
+#pragma unroll
+    for (int m = 0; m < kCellWarps; ++m) {
+      const int c = m * 32 + lane, ty = c / kPatchX, tx = c % kPatchX;
+      int s = 0, e = 0;
+      if (ty < nr && tx < nx) {
+        const int g = cell_base + (r0 + ty) * p.X + x0 + tx;
+        s = __ldg(p.cell_start + g);
+        e = __ldg(p.cell_start + g + 1);
+      }
+      len[m] = e - s;
+      if (m == warp) lo_mine = s;
+    }
+    int len_mine = 0;
+#pragma unroll
+    for (int m = 0; m < kCellWarps; ++m)
+      if (m == warp) len_mine = len[m];
+    const int mine = warp * 32 + lane;
+    int rank = 0;  // position in the order: length descending, ties by cell index
+#pragma unroll
+    for (int m = 0; m < kCellWarps; ++m) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int o = __shfl_sync(kFull, len[m], k);
+        rank += (o > len_mine || (o == len_mine && m * 32 + k < mine)) ? 1 : 0;
+      }
+    }
+    s_lo[mine] = lo_mine, s_hi[mine] = lo_mine + len_mine;
+    s_order[rank] = (unsigned char)mine;
   }
-  const char *feat_q = static_cast<const char *>(p.feat) + (size_t)l * 4 * sizeof(FeatT);
-  asm volatile("" : "+l"(feat_q));  // keep the per-lane base in a register pair (one IMAD.WIDE per row)
-  const size_t qstep = (size_t)lanes * 4 * sizeof(FeatT);
+  if (to_tile) {  // empty cells are never visited: their zeros are written here
+    float4 *t4 = reinterpret_cast<float4 *>(cells_ts);
+    for (int i = tid; i < (p.C * kTilePitch + 3) / 4; i += 32 * kFwdWarps) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+
+  const bool active = lane < lanes;
+  const char *feat_q = static_cast<const char *>(p.feat) + (size_t)(active ? lane : 0) * 4 * sizeof(FeatT);
+  asm volatile("" : "+l"(feat_q));  // the per-lane base stays in a register pair: one IMAD.WIDE per row
+  const unsigned qstep = (unsigned)lanes * 4 * sizeof(FeatT);
+  const unsigned row_bytes = p.row_bytes;
+  const unsigned lt = lanemask_lt();
+  uint2 *my_ent = s_ent[warp];
+
+  // ---- this warp's chunks, in order: cells of the snake schedule, 32 points at a time -----------
+  int it_round = 0, it_cell = 0, it_base = 0, it_end = 0;
+  auto fetch = [&]() -> FwdChunk {  // stage 1: next chunk + its index loads
+    FwdChunk c;
+    c.n = -1, c.cell = 0, c.last = 0, c.rf = -1 - lane, c.rd = 0, c.w = 0.f;
+    if (it_base >= it_end) {  // next non-empty cell (the order ends with the empty ones)
+      if (it_round >= kFwdRounds) return c;
+#ifndef RCB_FWD_STATIC
+      int item = 0;
+      if (lane == 0)
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(item) : "r"((unsigned)__cvta_generic_to_shared(&s_next)) : "memory");
+      item = __shfl_sync(kFull, item, 0);
+      if (item >= kPatchCells) {
+        it_round = kFwdRounds;
+        return c;
+      }
+#else
+      const int item = it_round * kFwdWarps + ((it_round & 1) ? kFwdWarps - 1 - warp : warp);
+      ++it_round;
+#endif
+      it_cell = s_order[item];
+      it_base = s_lo[it_cell], it_end = s_hi[it_cell];
+      if (it_base >= it_end) {
+        it_round = kFwdRounds;
+        return c;
+      }
+    }
+    c.cell = it_cell;
+    c.n = min(32, it_end - it_base);
+    if (lane < c.n) {
+      c.rf = ld_stream_s32(p.ranks_feat + it_base + lane);
+      c.rd = ld_stream_s32(p.ranks_depth + it_base + lane);
+    }
+    it_base += 32;
+    c.last = it_base >= it_end;
+#ifdef RCB_FWD_NOPIPE
+    if (lane < c.n) c.w = ld_stream_f32(p.depth + c.rd);
+#endif
+    return c;
+  };
+  auto gather = [&](FwdChunk &c) {  // stage 2: depth weights
+#ifndef RCB_FWD_NOPIPE
+    if (lane < c.n) c.w = ld_stream_f32(p.depth + c.rd);
+#endif
+  };
 
   float4 acc[kQ];
 #pragma unroll
   for (int j = 0; j < kQ; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  auto take = [&](const uint2 ev, float4 (&v)[kQ]) {  // issue the row loads of one entry
-    if (ev.x != kSkipEntry) {
-#pragma unroll
-      for (int j = 0; j < kQ; ++j) v[j] = Row4<FeatT>::load_bytes(feat_q + ev.x + j * qstep);
-    }
-  };
-  auto fold = [&](const uint2 ev, const float4 (&v)[kQ]) {
-    if (ev.x != kSkipEntry) {
-      const float w = __uint_as_float(ev.y);
-#pragma unroll
-      for (int j = 0; j < kQ; ++j) cells_fma(acc[j], v[j], w);
-    }
-  };
+#ifdef RCB_FWD_NOPIPE
+  FwdChunk c1 = fetch();
+  while (c1.n >= 0) {
+    const FwdChunk c0 = c1;
+#else
+  FwdChunk c2 = fetch();
+  FwdChunk c1 = c2;
+  gather(c1);
+  c2 = fetch();
+  while (c1.n >= 0) {
+    const FwdChunk c0 = c1;
+    c1 = c2;
+    gather(c1);
+    c2 = fetch();
+#endif
 
-  int i = s;
-  if ((i & 1) && i < e) {  // entries are fetched in 16-byte pairs: peel an odd first one
-    const uint2 ev = __ldg(p.entries + i);
-    float4 v[kQ];
-    take(ev, v);
-    fold(ev, v);
-    ++i;
-  }
-  constexpr int kPairs = 2;  // 4 entries (rows) in flight per thread
-  for (; i + 2 * kPairs <= e; i += 2 * kPairs) {
-    uint4 pr[kPairs];
-    float4 v[2 * kPairs][kQ];
+    // ---- stage 3, lane <-> point: merge the points of one row, compact the entries --------------
+    const int rf = c0.rf;
+    const int rf_prev = __shfl_up_sync(kFull, rf, 1);
+    const unsigned starts = __ballot_sync(kFull, lane == 0 || rf != rf_prev);
+    const int run_head = 31 - __clz((int)(starts & (0xffffffffu >> (31 - lane))));
+    const int pos = (lane - run_head) & 3;  // position inside a group of <= 4 points of one row
+    float w_sum = c0.w;
 #pragma unroll
-    for (int u = 0; u < kPairs; ++u) pr[u] = __ldg(reinterpret_cast<const uint4 *>(p.entries + i) + u);
-#pragma unroll
-    for (int u = 0; u < kPairs; ++u) {
-      take(make_uint2(pr[u].x, pr[u].y), v[2 * u]);
-      take(make_uint2(pr[u].z, pr[u].w), v[2 * u + 1]);
+    for (int k = 1; k < 4; ++k) {
+      const float wk = __shfl_down_sync(kFull, c0.w, k);
+      const int pk = __shfl_down_sync(kFull, pos, k);
+      if (lane + k < 32 && pk == k) w_sum += wk;  // lane + k is the k-th follower of my group
     }
+    const bool is_head = lane < c0.n && pos == 0;
+    const unsigned heads = __ballot_sync(kFull, is_head);
+    const int n_ent = __popc(heads);
+    if (is_head) my_ent[__popc(heads & lt)] = make_uint2((unsigned)rf, __float_as_uint(w_sum));
+    __syncwarp();
+
+    // ---- lane <-> channel quad: rows through L1, kRows in flight ----------------------------------
+    if (active) {
+      int j = 0;
+      for (; j + kRows <= n_ent; j += kRows) {
+        uint2 e1[kRows];
+        float4 v[kRows][kQ];
 #pragma unroll
-    for (int u = 0; u < kPairs; ++u) {
-      fold(make_uint2(pr[u].x, pr[u].y), v[2 * u]);
-      fold(make_uint2(pr[u].z, pr[u].w), v[2 * u + 1]);
+        for (int u = 0; u < kRows; u += 2) {
+          const uint4 e2 = *reinterpret_cast<const uint4 *>(my_ent + j + u);
+          e1[u] = make_uint2(e2.x, e2.y), e1[u + 1] = make_uint2(e2.z, e2.w);
+        }
+#pragma unroll
+        for (int u = 0; u < kRows; ++u) {
+          const char *row = feat_q + (size_t)e1[u].x * row_bytes;
+#pragma unroll
+          for (int q = 0; q < kQ; ++q) v[u][q] = Row4<FeatT>::load_bytes(row + q * qstep);
+        }
+#pragma unroll
+        for (int u = 0; u < kRows; ++u) {
+#pragma unroll
+          for (int q = 0; q < kQ; ++q) cells_fma(acc[q], v[u][q], __uint_as_float(e1[u].y));
+        }
+      }
+      if (j < n_ent) {  // the last, partial group: same shape, loads predicated (warp-uniform)
+        uint2 e1[kRows];
+        float4 v[kRows][kQ];
+#pragma unroll
+        for (int u = 0; u < kRows - 1; ++u) {
+          if (j + u < n_ent) {
+            e1[u] = my_ent[j + u];
+            const char *row = feat_q + (size_t)e1[u].x * row_bytes;
+#pragma unroll
+            for (int q = 0; q < kQ; ++q) v[u][q] = Row4<FeatT>::load_bytes(row + q * qstep);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kRows - 1; ++u) {
+          if (j + u < n_ent) {
+#pragma unroll
+            for (int q = 0; q < kQ; ++q) cells_fma(acc[q], v[u][q], __uint_as_float(e1[u].y));
+          }
+        }
+      }
+      if (c0.last) {  // the cell's row: straight out (channels last) or into the transpose tile
+        if (to_tile) {
+#pragma unroll
+          for (int q = 0; q < kQ; ++q) {
+            float *col = cells_ts + 4 * (lane + q * lanes) * kTilePitch + c0.cell;
+            col[0] = acc[q].x, col[kTilePitch] = acc[q].y, col[2 * kTilePitch] = acc[q].z, col[3 * kTilePitch] = acc[q].w;
+          }
+        } else {
+          const int cty = c0.cell / kPatchX, ctx = c0.cell % kPatchX;
+          float4 *dst = reinterpret_cast<float4 *>(p.out + (size_t)(cell_base + (r0 + cty) * p.X + x0 + ctx) * p.C);
+#pragma unroll
+          for (int q = 0; q < kQ; ++q) st_stream_f4(dst + lane + q * lanes, acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < kQ; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
-  }
-  for (; i < e; ++i) {
-    const uint2 ev = __ldg(p.entries + i);
-    float4 v[kQ];
-    take(ev, v);
-    fold(ev, v);
+    __syncwarp();  // the next chunk rewrites the entries
+#ifdef RCB_FWD_NOPIPE
+    c1 = fetch();
+#endif
   }
 
-  // ---- write the whole patch, empty cells included ------------------------------------------------
-  if (p.layout == RCB_LAYOUT_CELLS_C) {
-    if (cell_ok) {
-      float4 *dst = reinterpret_cast<float4 *>(p.out + (size_t)gcell * p.C);
+  if (!to_tile) {  // channels last: the empty cells' zeros, cell <-> warp round-robin
+    if (active) {
+      for (int c = warp; c < kPatchCells; c += kFwdWarps) {
+        const int cty = c / kPatchX, ctx = c % kPatchX;
+        if (s_hi[c] > s_lo[c] || cty >= nr || ctx >= nx) continue;
+        float4 *dst = reinterpret_cast<float4 *>(p.out + (size_t)(cell_base + (r0 + cty) * p.X + x0 + ctx) * p.C);
 #pragma unroll
-      for (int j = 0; j < kQ; ++j) st_stream_f4(dst + l + j * lanes, acc[j]);
+        for (int q = 0; q < kQ; ++q) st_stream_f4(dst + lane + q * lanes, make_float4(0.f, 0.f, 0.f, 0.f));
+      }
     }
     return;
   }
-  // (B, C, cells): transpose through shared memory, then every store instruction writes kCellsTileY
-  // runs of kCellsTileX consecutive cells of one channel row
-#pragma unroll
-  for (int j = 0; j < kQ; ++j) {
-    const int c0 = 4 * (l + j * lanes);
-    cells_ts[(c0 + 0) * 33 + cell] = acc[j].x, cells_ts[(c0 + 1) * 33 + cell] = acc[j].y;
-    cells_ts[(c0 + 2) * 33 + cell] = acc[j].z, cells_ts[(c0 + 3) * 33 + cell] = acc[j].w;
-  }
+
+  // (B, C, cells): every store instruction writes 32 / kPatchX runs of kPatchX consecutive cells of
+  // one channel row
   __syncthreads();
-  const int ty = lane / kCellsTileX, tx = lane % kCellsTileX;
-  if (ty < nr && tx < nx) {
-    float *dst = p.out + (size_t)b * p.C * p.cells_per_sample + (size_t)(r0 + ty) * p.X + x0 + tx;
-    for (int ch = warp; ch < p.C; ch += n_warps) st_stream_f32(dst + (size_t)ch * p.cells_per_sample, cells_ts[ch * 33 + lane]);
+  float *dst_b = p.out + (size_t)b * p.C * p.cells_per_sample;
+#pragma unroll
+  for (int m = 0; m < kCellWarps; ++m) {
+    const int c = m * 32 + lane, ty = c / kPatchX, tx = c % kPatchX;
+    if (ty >= nr || tx >= nx) continue;
+    float *dst = dst_b + (size_t)(r0 + ty) * p.X + x0 + tx;
+    const float *src = cells_ts + c;
+    for (int ch = warp; ch < p.C; ch += kFwdWarps)
+      st_stream_f32(dst + (size_t)ch * p.cells_per_sample, src[ch * kTilePitch]);
   }
 }
 
 template <typename FeatT, int kLanes, int kQ>
-static int launch_cells_t(const FwdCellsParams &p, int lanes, long long grid, cudaStream_t s) {
-  const size_t smem = p.layout == RCB_LAYOUT_B_C_CELLS ? (size_t)p.C * 33 * 4 : 0;
-  if (smem > 48 * 1024)
+static int launch_cells_t(const FwdCellsParams &p, long long grid, cudaStream_t s) {
+  const size_t smem = p.layout == RCB_LAYOUT_B_C_CELLS ? align_up((size_t)p.C * kTilePitch * 4, 16) : 0;
+  if (smem > 40 * 1024)
     RCB_CUDA_TRY(cudaFuncSetAttribute(k_fwd_cells<FeatT, kLanes, kQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  RCB_CUDA_TRY(launch_pdl(k_fwd_cells<FeatT, kLanes, kQ>, (unsigned)grid, 32 * lanes, smem, s, p));
+#ifdef RCB_FWD_CARVEOUT
+  RCB_CUDA_TRY(cudaFuncSetAttribute(k_fwd_cells<FeatT, kLanes, kQ>, cudaFuncAttributePreferredSharedMemoryCarveout, RCB_FWD_CARVEOUT));
+#endif
+  RCB_CUDA_TRY(launch_pdl(k_fwd_cells<FeatT, kLanes, kQ>, (unsigned)grid, 32 * kFwdWarps, smem, s, p));
   return RCB_OK;
 }
 
@@ -205,13 +364,13 @@ static int launch_cells(const FwdCellsParams &p, long long grid, cudaStream_t s)
   const int C = p.C;
   if (C <= 128) {  // one quad per lane
     switch (C / 4) {
-      case 16: return launch_cells_t<FeatT, 16, 1>(p, 16, grid, s);
-      case 20: return launch_cells_t<FeatT, 20, 1>(p, 20, grid, s);
-      case 32: return launch_cells_t<FeatT, 32, 1>(p, 32, grid, s);
-      default: return launch_cells_t<FeatT, 0, 1>(p, C / 4, grid, s);
+      case 16: return launch_cells_t<FeatT, 16, 1>(p, grid, s);
+      case 20: return launch_cells_t<FeatT, 20, 1>(p, grid, s);
+      case 32: return launch_cells_t<FeatT, 32, 1>(p, grid, s);
+      default: return launch_cells_t<FeatT, 0, 1>(p, grid, s);
     }
   }
-  return launch_cells_t<FeatT, 0, 2>(p, C / 8, grid, s);  // two quads per lane
+  return launch_cells_t<FeatT, 0, 2>(p, grid, s);  // two quads per lane
 }
 
 // Sorted cells with a CSR, whole 128-bit quads per lane, 32-bit row offsets.
@@ -224,29 +383,16 @@ bool fwd_cells_eligible(const rcb_pool_desc *d, const void *feat, const int *cel
   return true;
 }
 
-size_t fwd_cells_workspace_bytes(const rcb_pool_desc *d) { return align_up((size_t)max(d->n_points, 1) * 8 + 16, 256); }
-
 int fwd_cells_launch(const rcb_pool_desc *d, const float *depth, const void *feat, const int *ranks_depth,
-                     const int *ranks_feat, const int *ranks_bev, const int *cell_start, float *out,
-                     void *workspace, size_t workspace_bytes, int sms, cudaStream_t s) {
-  if (!workspace || workspace_bytes < fwd_cells_workspace_bytes(d)) return RCB_ERR_WORKSPACE;
-  if (((uintptr_t)workspace) % 16) return RCB_ERR_ALIGN;
+                     const int *ranks_feat, const int *cell_start, float *out, cudaStream_t s) {
   const int elem = d->feat_dtype == RCB_DTYPE_F32 ? 4 : 2;
-  const int n_cells = d->B * d->Z * d->Y * d->X;
-  FwdEntriesParams ep;
-  ep.depth = depth, ep.ranks_depth = ranks_depth, ep.ranks_feat = ranks_feat, ep.ranks_bev = ranks_bev;
-  ep.n_ptr = cell_start + n_cells;
-  ep.entries = static_cast<uint2 *>(workspace);
-  ep.row_bytes = (unsigned)d->C * elem;
-  if (d->n_points > 0) {
-    const int grid = max(1, min(ceil_div(d->n_points, 256), sms * 16));
-    RCB_CUDA_TRY(launch_pdl(k_fwd_entries, grid, 256, 0, s, ep));
-  }
   FwdCellsParams p;
-  p.feat = feat, p.entries = ep.entries, p.cell_start = cell_start, p.out = out;
+  p.depth = depth, p.feat = feat, p.ranks_depth = ranks_depth, p.ranks_feat = ranks_feat;
+  p.cell_start = cell_start, p.out = out;
   p.C = d->C, p.X = d->X, p.R = d->Z * d->Y;
-  p.tiles_x = ceil_div(p.X, kCellsTileX), p.tiles_r = ceil_div(p.R, kCellsTileY);
+  p.tiles_x = ceil_div(p.X, kPatchX), p.tiles_r = ceil_div(p.R, kPatchY);
   p.cells_per_sample = d->Z * d->Y * d->X, p.layout = d->layout, p.B = d->B;
+  p.row_bytes = (unsigned)d->C * elem;
   p.by_B = FastDiv::make((unsigned)p.B), p.by_tiles_x = FastDiv::make((unsigned)p.tiles_x);
   const long long grid = (long long)d->B * p.tiles_r * p.tiles_x;
   switch (d->feat_dtype) {
