@@ -54,3 +54,11 @@ def test_gpu_arm_prints_one_json_line_with_roofline():
     assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0
     assert e2e["value"] < d["value"]  # host copies inside the timed region
     assert set(d["stages_ms"]) == {"prepare", "feat_rows", "fwd", "og_rows", "bwd"}
+    # the e2e step ships the calibration, not a materialised coor
+    assert e2e["h2d_bytes_per_step"] < d["e2e_coor_input"]["h2d_bytes_per_step"] - 40e6
+    assert d["clocks"]["samples_pre_spin"] > 20
+    cfg = d["configs"]
+    assert "error" not in cfg, cfg
+    for name in ("temporal_8f", "hires_256_B1", "hires_256_B8", "radar_128", "radar_512"):
+        assert cfg[name]["samples_per_s"] > 0, name
+    assert "prepare_torch_ms" in d["reference_gpu"]

@@ -117,3 +117,51 @@ def test_full_size_digest_against_live_reference():
     assert out[0].shape[0] == dg["K"] and out[3].shape[0] == dg["I"]
     for k, a in zip(("ranks_bev", "ranks_depth", "ranks_feat", "interval_starts", "interval_lengths"), out):
         assert hashlib.sha256(a.tobytes()).hexdigest() == dg["sha256"][k], k
+
+
+@pytest.mark.parametrize("name", PREP_CASES + ["emptyC"])
+def test_torch_restatement_matches_reference_golden(golden_prepare, name):
+    """oracle/torch_ref.py (the formulation bench.py times as "the reference's PyTorch path") gives
+    the reference's own outputs: tie-independent arrays as they come, the others canonicalised."""
+    import torch
+    from oracle import torch_ref
+    g = golden_prepare
+    out = torch_ref.prepare(torch.from_numpy(g[f"{name}.coor"]), g[f"{name}.lower"], g[f"{name}.interval"],
+                            g[f"{name}.size"])
+    if int(g[f"{name}.empty"]):
+        assert out == (None,) * 5
+        return
+    rb, rd, rf, st, ln = (t.numpy() for t in out)
+    assert np.array_equal(rb, g[f"{name}.raw.ranks_bev"])
+    assert np.array_equal(st, g[f"{name}.raw.interval_starts"])
+    assert np.array_equal(ln, g[f"{name}.raw.interval_lengths"])
+    crb, crd, crf = oracle.canonicalise(rb, rd, rf)
+    assert np.array_equal(crd, g[f"{name}.canon.ranks_depth"]) and np.array_equal(crf, g[f"{name}.canon.ranks_feat"])
+
+
+def test_torch_pool_restatement_kat_and_oracle(golden_prepare):
+    """index_add_ restatement: the reference's known-answer test (bev_pool.py:145-176) through
+    autograd, and agreement with the C oracle on a golden geometry."""
+    import torch
+    from oracle import torch_ref
+    depth = torch.tensor([0.3, 0.4, 0.2, 0.1, 0.7, 0.6, 0.8, 0.9]).view(1, 1, 2, 2, 2).requires_grad_(True)
+    feat = torch.ones(1, 1, 2, 2, 2, requires_grad=True)
+    t = lambda a: torch.tensor(a, dtype=torch.int32)
+    bev = torch_ref.pool(depth, feat, t([0, 4, 1, 6]), t([0, 0, 1, 2]), t([0, 0, 1, 1]), (1, 1, 2, 2, 2))
+    loss = bev.sum()
+    loss.backward()
+    assert abs(float(loss) - 4.4) < 1e-6
+    assert torch.allclose(depth.grad.flatten(), torch.tensor([2., 2., 0., 0., 2., 0., 2., 0.]))
+    assert torch.allclose(feat.grad.flatten(), torch.tensor([1.0, 1.0, 0.4, 0.4, 0.8, 0.8, 0., 0.]))
+    g = golden_prepare
+    coor = g["augD.coor"]
+    B, N, D, H, W, _ = coor.shape
+    rb, rd, rf, st, ln = oracle.voxel_pooling_prepare_v2(coor, g["augD.lower"], g["augD.interval"], g["augD.size"])
+    gx, gy, gz = (int(v) for v in g["augD.size"])
+    rng = np.random.default_rng(5)
+    dep = rng.random((B, N, D, H, W), dtype=np.float32)
+    rows = rng.standard_normal((B, N, H, W, 16), dtype=np.float32)
+    want = oracle.to_bczyx(oracle.bev_pool_v2_forward(dep, rows, rd, rf, rb, (B, gz, gy, gx, 16), st, ln))
+    got = torch_ref.pool(torch.from_numpy(dep), torch.from_numpy(rows), torch.from_numpy(rd), torch.from_numpy(rf),
+                         torch.from_numpy(rb), (B, gz, gy, gx, 16)).numpy()
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
