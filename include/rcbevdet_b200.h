@@ -216,6 +216,38 @@ int rcb_radar_rcs_scatter(const rcb_radar_desc *d, const float *point_features, 
 int rcb_radar_scatter_bwd(const rcb_radar_desc *d, const float *features_grad, const int *coors,
                           float *point_features_grad, int device, rcb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * SURVEY.md 8(f-3) -- BEVDepth4D.gen_grid + shift_feature
+ *   (mmdet3d/models/detectors/bevdet_rc.py:585-657): temporal alignment of a pooled BEV feature map.
+ * input / output (n, C, H, W) float32 contiguous; tf [n][9]: row-major 3x3 that maps a key-frame BEV
+ * pixel (x, y, 1) to the adjacent frame's pixel (the `tf` of bevdet_rc.py:642).  Per output pixel:
+ * p = tf * (x, y, 1); normalise by (W-1, H-1) to [-1, 1] (:646-650); grid_sample's align_corners=True
+ * un-normalisation; bilinear taps, zero padding -- one kernel, no grid tensor.
+ * The backward is the gradient w.r.t. `input` (float atomics, like grid_sample's); input_grad is
+ * zero-filled inside.
+ * ------------------------------------------------------------------------------------------ */
+int rcb_bev_shift_feature(const float *input, const float *tf, float *output, int n, int C, int H, int W,
+                          int device, rcb_stream_t stream);
+int rcb_bev_shift_feature_bwd(const float *output_grad, const float *tf, float *input_grad, int n, int C,
+                              int H, int W, int device, rcb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SURVEY.md 8(f-2) -- the producer of the pooling inputs, fused
+ *   (mmdet3d/models/necks/view_transformer.py:316-319 / :793-797: channel split of the depth-net
+ *    output + softmax over the depth bins; mmdet3d/ops/bev_pool_v2/bev_pool.py:21: channels-last copy
+ *    of the context).
+ * x: (n_img, >= D + C, H, W), `x_dtype` (RCB_DTYPE_*), image stride x_img_stride elements.
+ * depth (n_img, D, H, W) float32 = softmax over channels [0, D); context_rows (n_img * H * W, C)
+ * float32 = channels [D, D + C) channels last: the `feat` rows of rcb_bev_pool_v2_fwd.  D <= 256.
+ * Backward: x_grad (n_img, D + C, H, W) float32 from depth (the forward's output), depth_grad and
+ * context_rows_grad.
+ * ------------------------------------------------------------------------------------------ */
+int rcb_depth_context_split(const void *x, int x_dtype, float *depth, float *context_rows, int n_img, int D,
+                            int C, int HW, long long x_img_stride, int device, rcb_stream_t stream);
+int rcb_depth_context_split_bwd(const float *depth, const float *depth_grad, const float *context_rows_grad,
+                                float *x_grad, int n_img, int D, int C, int HW, int device,
+                                rcb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -182,6 +182,49 @@ def gen_radar():
     np.savez_compressed(os.path.join(GOLD, "radar_ref.npz"), **cases)
 
 
+def temporal_inputs(n, C, h, w, seed, with_bda_adj):
+    """Key / adjacent frame calibration of the deterministic rig (one camera is enough: gen_grid reads
+    camera 0 only), seeded BEV augmentation, seeded features."""
+    import math
+    from rcbevdet_b200 import rig
+    g = torch.Generator().manual_seed(seed)
+    motion = rig.temporal_motion(n, 2, seed=seed).view(n, 2, 3)
+    key = rig.camera_rig(n, frame_motion=motion[:, 0])[0]          # sensor2ego of the key frame (n, 6, 4, 4)
+    adj = rig.camera_rig(n, frame_motion=motion[:, 1] * 3.0)[0]    # adjacent frame, exaggerated ego motion
+    def bda(k):
+        ang = (torch.rand(n, generator=g) - 0.5) * 0.6
+        sc = 0.95 + 0.1 * torch.rand(n, generator=g)
+        m = torch.zeros(n, 3, 3)
+        m[:, 0, 0], m[:, 0, 1], m[:, 1, 0], m[:, 1, 1], m[:, 2, 2] = torch.cos(ang), -torch.sin(ang), torch.sin(ang), torch.cos(ang), 1.0
+        m = m * sc.view(n, 1, 1)
+        if k:
+            m[0, 1] = -m[0, 1]      # a flipped sample
+        return m
+    feats = torch.randn(n, C, h, w, generator=g)
+    return feats, [key, adj], bda(0), (bda(1) if with_bda_adj else None)
+
+
+def gen_temporal():
+    """BEVDepth4D.gen_grid / shift_feature (bevdet_rc.py:585-657) executed from the reference file."""
+    lo, iv = [-51.2, -51.2, -5.0], [0.8, 0.8, 8.0]
+    cases = {}
+    for name, (n, C, h, w, seed, adj) in {"t16": (2, 3, 16, 16, 3, False), "t32": (3, 5, 24, 32, 4, True),
+                                          "t128": (1, 2, 128, 128, 5, True)}.items():
+        scale = 128.0 / w                       # the 102.4 m grid at this resolution
+        iv_c = [iv[0] * scale, iv[1] * 128.0 / h, iv[2]]
+        ref = refload.load_temporal_alignment(iv_c, lo)
+        feats, s2k, bda, bda_adj = temporal_inputs(n, C, h, w, seed, adj)
+        grid = ref.gen_grid(feats, s2k, bda, bda_adj=bda_adj)
+        out = ref.shift_feature(feats, s2k, bda, bda_adj=bda_adj)
+        cases.update({f"{name}.input": _np(feats), f"{name}.key": _np(s2k[0]), f"{name}.adj": _np(s2k[1]),
+                      f"{name}.bda": _np(bda), f"{name}.interval": np.float32(iv_c), f"{name}.lower": np.float32(lo),
+                      f"{name}.grid": _np(grid), f"{name}.output": _np(out)})
+        if bda_adj is not None:
+            cases[f"{name}.bda_adj"] = _np(bda_adj)
+        print(name, tuple(out.shape), "covered", float((out.abs().sum(1) > 0).float().mean()))
+    np.savez_compressed(os.path.join(GOLD, "temporal_ref.npz"), **cases)
+
+
 if __name__ == "__main__":
     assert refload.available(), "reference tree not found"
     os.makedirs(GOLD, exist_ok=True)
@@ -190,5 +233,7 @@ if __name__ == "__main__":
     gen_prepare()
     print("radar:")
     gen_radar()
+    print("temporal:")
+    gen_temporal()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))

@@ -88,3 +88,44 @@ def load_bev_pool_py(ext_module):
     pkg.bev_pool_v2_ext = ext_module
     sys.modules["_rcb_ref_bev_pool_pkg.bev_pool_v2_ext"] = ext_module
     return _load("_rcb_ref_bev_pool_pkg.bev_pool", "mmdet3d/ops/bev_pool_v2/bev_pool.py")
+
+
+def load_temporal_alignment(grid_interval, grid_lower_bound):
+    """The reference's BEVDepth4D.gen_grid / shift_feature (mmdet3d/models/detectors/bevdet_rc.py:
+    585-657), executed from where they lie: the two method bodies are cut out of the file by line
+    (the module itself imports half of mmdet3d) and bound to a stand-in object that carries the
+    three attributes they read.  Returns an object with .gen_grid(...) and .shift_feature(...)."""
+    import ast
+    import textwrap
+    import types as _t
+
+    import torch
+    import torch.nn.functional as F
+
+    path = os.path.join(REF_ROOT, "mmdet3d/models/detectors/bevdet_rc.py")
+    with open(path) as f:
+        src = f.read()
+    tree = ast.parse(src)
+    lines = src.splitlines()
+    found = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ClassDef) and node.name == "BEVDepth4D_RC" or isinstance(node, ast.ClassDef):
+            for item in node.body:
+                if isinstance(item, ast.FunctionDef) and item.name in ("gen_grid", "shift_feature") \
+                        and item.name not in found:
+                    found[item.name] = textwrap.dedent("\n".join(lines[item.lineno - 1:item.end_lineno]))
+    if set(found) != {"gen_grid", "shift_feature"}:
+        raise RuntimeError("gen_grid / shift_feature not found in the reference")
+    ns = {"torch": torch, "F": F}
+    exec(found["gen_grid"], ns)
+    exec(found["shift_feature"], ns)
+    vt = _t.SimpleNamespace(grid_interval=torch.as_tensor(grid_interval, dtype=torch.float32),
+                            grid_lower_bound=torch.as_tensor(grid_lower_bound, dtype=torch.float32))
+
+    class _Stub:
+        grid = None
+        img_view_transformer = vt
+    stub = _Stub()
+    stub.gen_grid = _t.MethodType(ns["gen_grid"], stub)
+    stub.shift_feature = _t.MethodType(ns["shift_feature"], stub)
+    return stub

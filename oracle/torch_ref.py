@@ -56,3 +56,44 @@ def pool(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape):
     out = rows.new_zeros((B * Z * Y * X, C))                                                       # bev_pool.py:27
     out = out.index_add(0, ranks_bev.long(), w[:, None] * rows[ranks_feat.long()])                 # bev_pool_cuda.cu:21-48
     return out.view(B, Z, Y, X, C).permute(0, 4, 1, 2, 3).contiguous()                             # bev_pool.py:91
+
+
+def gen_grid(input, sensor2keyegos, bda, bda_adj, grid_interval, grid_lower_bound):
+    """BEVDepth4D.gen_grid (bevdet_rc.py:585-652) restated op for op: normalised sampling grid
+    (n, h, w, 2) that maps the key frame's BEV pixels into the adjacent frame's BEV."""
+    n, c, h, w = input.shape
+    xs = torch.linspace(0, w - 1, w, dtype=input.dtype, device=input.device).view(1, w).expand(h, w)   # :590-592
+    ys = torch.linspace(0, h - 1, h, dtype=input.dtype, device=input.device).view(h, 1).expand(h, w)   # :593-595
+    grid = torch.stack((xs, ys, torch.ones_like(xs)), -1)                                              # :596
+    grid = grid.view(1, h, w, 3).expand(n, h, w, 3).view(n, h, w, 3, 1)                                # :600
+    c02l0 = sensor2keyegos[0][:, 0:1, :, :]                                                            # :604
+    c12l0 = sensor2keyegos[1][:, 0:1, :, :]                                                            # :607
+    bda_ = torch.zeros((n, 1, 4, 4), dtype=grid.dtype).to(grid)                                        # :610-612
+    bda_[:, :, :3, :3] = bda.unsqueeze(1)
+    bda_[:, :, 3, 3] = 1
+    c02l0 = bda_.matmul(c02l0)                                                                         # :613
+    if bda_adj is not None:                                                                            # :614-617
+        bda_ = torch.zeros((n, 1, 4, 4), dtype=grid.dtype).to(grid)
+        bda_[:, :, :3, :3] = bda_adj.unsqueeze(1)
+        bda_[:, :, 3, 3] = 1
+    c12l0 = bda_.matmul(c12l0)                                                                         # :618
+    l02l1 = c02l0.matmul(torch.inverse(c12l0))[:, 0, :, :].view(n, 1, 1, 4, 4)                         # :622-623
+    keep = [True, True, False, True]
+    l02l1 = l02l1[:, :, :, keep, :][:, :, :, :, keep]                                                  # :631-633
+    feat2bev = torch.zeros((3, 3), dtype=grid.dtype).to(grid)                                          # :635-641
+    feat2bev[0, 0] = float(grid_interval[0])
+    feat2bev[1, 1] = float(grid_interval[1])
+    feat2bev[0, 2] = float(grid_lower_bound[0])
+    feat2bev[1, 2] = float(grid_lower_bound[1])
+    feat2bev[2, 2] = 1
+    feat2bev = feat2bev.view(1, 3, 3)
+    tf = torch.inverse(feat2bev).matmul(l02l1).matmul(feat2bev)                                        # :642
+    grid = tf.matmul(grid)                                                                             # :645
+    norm = torch.tensor([w - 1.0, h - 1.0], dtype=input.dtype, device=input.device)                    # :646-648
+    return grid[:, :, :, :2, 0] / norm.view(1, 1, 1, 2) * 2.0 - 1.0                                    # :649-650
+
+
+def shift_feature(input, sensor2keyegos, bda, bda_adj, grid_interval, grid_lower_bound):
+    """bevdet_rc.py:654-657."""
+    grid = gen_grid(input, sensor2keyegos, bda, bda_adj, grid_interval, grid_lower_bound)
+    return torch.nn.functional.grid_sample(input, grid.to(input.dtype), align_corners=True)

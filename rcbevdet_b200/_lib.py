@@ -61,6 +61,10 @@ SIGNATURES = {
     "rcb_radar_workspace_bytes": (_sz, [ctypes.POINTER(RadarDesc)]),
     "rcb_radar_rcs_scatter": (_i, [ctypes.POINTER(RadarDesc)] + [_vp] * 6 + [_vp, _sz, _i, _vp]),
     "rcb_radar_scatter_bwd": (_i, [ctypes.POINTER(RadarDesc), _vp, _vp, _vp, _i, _vp]),
+    "rcb_bev_shift_feature": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rcb_bev_shift_feature_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rcb_depth_context_split": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _ll, _i, _vp]),
+    "rcb_depth_context_split_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lib = None

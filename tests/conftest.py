@@ -38,3 +38,9 @@ def golden_prepare():
 def golden_radar():
     import numpy as np
     return np.load(os.path.join(GOLDEN, "radar_ref.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_temporal():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "temporal_ref.npz"))
