@@ -248,6 +248,23 @@ int rcb_depth_context_split_bwd(const float *depth, const float *depth_grad, con
                                 float *x_grad, int n_img, int D, int C, int HW, int device,
                                 rcb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * SURVEY.md 8(f-4) -- the body of the TensorRT plugin `mmdeploy::bev_pool_v2`
+ *   (ONNX node: mmdet3d/ops/bev_pool_v2/bev_pool.py:98-119; eager twin :121-142; engine tools
+ *    tools/convert_bevdet_to_TRT.py:357-364).  Shaped like IPluginV2DynamicExt::enqueue /
+ *   getWorkspaceSize: device pointers in ONNX input order -- inputs[0..6] = depth (N,D,H,W) f32,
+ *   feat (N,H,W,C) `feat_dtype`, ranks_depth, ranks_feat, ranks_bev, interval_starts,
+ *   interval_lengths (int32) -- outputs[0] = (1, out_height, out_width, C) f32, fully written.
+ *   No allocation, no host synchronisation.  sorted_cells = 1 asserts that the interval cells are
+ *   strictly increasing (ranks from voxel_pooling_prepare_v2): cell-stationary kernel, CSR rebuilt
+ *   in `workspace`; 0: general kernel for any ranks.  INTEGRATION.md has the C++ plugin shell.
+ * ------------------------------------------------------------------------------------------ */
+size_t rcb_trt_bev_pool_v2_workspace_bytes(int out_height, int out_width, int sorted_cells);
+int rcb_trt_bev_pool_v2_enqueue(const void *const *inputs, void *const *outputs, int n_cams, int D, int H,
+                                int W, int C, int n_points, int n_intervals, int out_height, int out_width,
+                                int feat_dtype, int sorted_cells, void *workspace, size_t workspace_bytes,
+                                int device, rcb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,8 @@ SIGNATURES = {
     "rcb_bev_shift_feature": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rcb_bev_shift_feature_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rcb_depth_context_split": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _ll, _i, _vp]),
+    "rcb_trt_bev_pool_v2_workspace_bytes": (_sz, [_i, _i, _i]),
+    "rcb_trt_bev_pool_v2_enqueue": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp)] + [_i] * 11 + [_vp, _sz, _i, _vp]),
     "rcb_depth_context_split_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 

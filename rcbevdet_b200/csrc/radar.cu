@@ -7,9 +7,9 @@
 //   heatmap[cell]      = max over pillars covering the cell of G_r(dx, dy)        (max is commutative)
 //   heatmap_feat[cell] = rcs value of the LAST pillar (largest index) covering the cell
 // so the loop becomes one splat kernel with integer atomicMax (non-negative floats order like
-// their bit patterns) -- exact and deterministic -- followed by one dense write kernel that
-// produces all three outputs, zeros included, with coalesced rows (no memset of the outputs,
-// no per-pillar host sync).
+// their bit patterns) -- deterministic -- followed by one dense write kernel that produces all
+// three outputs, zeros included, with coalesced rows (no memset of the outputs, no per-pillar
+// host sync).
 #include "common.cuh"
 
 namespace rcb {
@@ -28,42 +28,148 @@ __device__ __forceinline__ int rcs_radius(const float *rcs_row, int rcs_dim) {
   return (int)rad;
 }
 
+// Splat: one CTA per group of kSplatPillars pillars; for each pillar the ROWS of its window are dealt
+// to the CTA's eight warps.  A pillar's window is (2r+1)^2 cells with r in [1, 56] on the config-4
+// distribution (780 cells on average): a warp per pillar (round 1) left a 3000x imbalance between
+// warps.  Here a CTA's warps share every pillar, and the hardware scheduler balances the groups.
+//
+// Two cuts of the per-cell cost:
+//  * exp(-(dx^2 + dy^2) / 2 sigma^2) = E[|dx|] * E[|dy|] with E[k] = exp(-k^2 / 2 sigma^2) tabulated
+//    per pillar in float64 (r + 1 exponentials instead of (2r+1)^2): the float64 product differs
+//    from the direct exponential by ~2 ulp(float64), i.e. it rounds to a different float32 for
+//    ~1e-8 of the values -- inside the <= 1 ulp(float32) contract of the heat-map.
+//    Offsets beyond the table (window clipped by a huge grid) take the direct exponential.
+//  * a cell is covered by ~136 pillars, and both reductions are maxima: most updates lose.  A plain
+//    load at L2 (possibly stale: values only grow, so a stale read can only cause a redundant
+//    atomic, never a wrong skip) filters them; groups run from the LAST pillar down, so that for
+//    last_cover (larger index wins) nearly every later update is filtered, too.
+// Both planes store value + 1 / bit patterns with 0 = "nothing yet": one memset clears the workspace.
+constexpr int kSplatPillars = 4;
+constexpr int kSplatTable = 512;  // tabulated offsets per pillar
+
 __global__ void __launch_bounds__(256) k_radar_splat(RadarParams p, const float *__restrict__ rcs,
                                                      const int *__restrict__ coors,
                                                      int *__restrict__ pillar_at,
                                                      int *__restrict__ last_cover,
                                                      int *__restrict__ heat_bits) {
-  const int lane = lane_id();
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < p.V; v += warps) {
-    const int b = __ldg(coors + v * 4), y = __ldg(coors + v * 4 + 2), x = __ldg(coors + v * 4 + 3);
-    if (b < 0 || b >= p.B || y < 0 || y >= p.ny || x < 0 || x >= p.nx) continue;
-    const int base = b * p.cells;
-    if (lane == 0) atomicMax(pillar_at + base + y * p.nx + x, v);
-    const int radius = rcs_radius(rcs + (size_t)v * p.rcs_dim, p.rcs_dim);
-    // gaussian.py:40-47: clipped window
-    const int left = min(x, radius), right = min(p.nx - x, radius + 1);
-    const int top = min(y, radius), bottom = min(p.ny - y, radius + 1);
-    const int w = left + right, h = top + bottom;
-    // gaussian.py:17-23 with sigma = diameter / 6 (gaussian.py:38-39), all float64
-    const double diameter = 2.0 * (double)radius + 1.0;
-    const double sigma = diameter / 6.0;
-    const double denom = 2.0 * sigma * sigma;
-    const double eps = 2.220446049250313e-16;  // np.finfo(float64).eps * h.max(), h.max() == 1
-    for (int i = lane; i < w * h; i += 32) {
-      const int iy = i / w, ix = i - iy * w;
-      const int dy = iy - top, dx = ix - left;
-      double g = exp(-(double)(dx * dx + dy * dy) / denom);
-      if (g < eps) g = 0.0;
-      const int cell = base + (y + dy) * p.nx + (x + dx);
-      atomicMax(heat_bits + cell, __float_as_int((float)g));
-      atomicMax(last_cover + cell, v);
+  __shared__ double s_exp[kSplatPillars][kSplatTable];
+  __shared__ int s_x[kSplatPillars], s_y[kSplatPillars], s_left[kSplatPillars], s_top[kSplatPillars];
+  __shared__ int s_w[kSplatPillars], s_h[kSplatPillars], s_base[kSplatPillars], s_v[kSplatPillars];
+  __shared__ double s_denom[kSplatPillars];
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int n_groups = ceil_div(p.V, kSplatPillars);
+  const double eps = 2.220446049250313e-16;  // np.finfo(float64).eps * h.max(), h.max() == 1
+  for (int group = n_groups - 1 - (int)blockIdx.x; group >= 0; group -= gridDim.x) {
+    __syncthreads();  // the previous group's tables are no longer read
+    if (warp < kSplatPillars) {
+      const int v = group * kSplatPillars + warp;
+      int rows = 0;
+      if (v < p.V) {
+        const int b = __ldg(coors + v * 4), y = __ldg(coors + v * 4 + 2), x = __ldg(coors + v * 4 + 3);
+        if (b >= 0 && b < p.B && y >= 0 && y < p.ny && x >= 0 && x < p.nx) {
+          const int base = b * p.cells;
+          if (lane == 0) atomicMax(pillar_at + base + y * p.nx + x, v + 1);
+          const int radius = rcs_radius(rcs + (size_t)v * p.rcs_dim, p.rcs_dim);
+          // gaussian.py:40-47: clipped window
+          const int left = min(x, radius), right = min(p.nx - x, radius + 1);
+          const int top = min(y, radius), bottom = min(p.ny - y, radius + 1);
+          // gaussian.py:17-23 with sigma = diameter / 6 (gaussian.py:38-39), all float64
+          const double diameter = 2.0 * (double)radius + 1.0;
+          const double sigma = diameter / 6.0;
+          const double denom = 2.0 * sigma * sigma;
+          const int reach = min(kSplatTable - 1, max(max(left, right - 1), max(top, bottom - 1)));
+          for (int k = lane; k <= reach; k += 32) s_exp[warp][k] = exp(-(double)(k * k) / denom);
+          if (lane == 0) {
+            s_x[warp] = x, s_y[warp] = y, s_left[warp] = left, s_top[warp] = top, s_w[warp] = left + right;
+            s_base[warp] = base, s_v[warp] = v + 1, s_denom[warp] = denom;
+          }
+          rows = top + bottom;
+        }
+      }
+      if (lane == 0) s_h[warp] = rows;
+    }
+    __syncthreads();
+    // pillar by pillar, the rows of its window dealt to the eight warps: everything that depends on the
+    // pillar lives in registers across its rows, a row costs its factor E[|dy|] and one address, a
+    // cell one table read, one product and two filtered maxima
+#pragma unroll 1
+    for (int i = 0; i < kSplatPillars; ++i) {
+      const int h = s_h[i];
+      if (h == 0) continue;
+      const int w = s_w[i], left = s_left[i], top = s_top[i];
+      const int v1 = s_v[i];
+      const double *tab = s_exp[i];
+      int *heat0 = heat_bits + s_base[i] + (s_y[i] - top) * p.nx + (s_x[i] - left);
+      int *last0 = last_cover + (heat0 - heat_bits);
+      for (int iy = warp; iy < h; iy += 8) {
+        const int dy = iy - top;
+        const int ay = abs(dy);
+        const double ey = ay < kSplatTable ? tab[ay] : -1.0;
+        int *heat = heat0 + iy * p.nx, *last = last0 + iy * p.nx;
+        for (int ix = lane; ix < w; ix += 32) {
+          const int dx = ix - left;
+          const int ax = abs(dx);
+          double g;
+          if (ey >= 0.0 && ax < kSplatTable) g = tab[ax] * ey;
+          else g = exp(-(double)((long long)dx * dx + (long long)dy * dy) / s_denom[i]);
+          if (g < eps) g = 0.0;
+          const int bits = __float_as_int((float)g);  // non-negative floats order like their bit patterns
+          // (read at L2, where the atomics execute: a line cached in this SM's L1 would stay stale and
+          // let every update through)
+          if (bits > __ldcg(heat + ix)) atomicMax(heat + ix, bits);
+          if (v1 > __ldcg(last + ix)) atomicMax(last + ix, v1);
+        }
+      }
     }
   }
 }
 
-// 32 consecutive cells x all channels per CTA; pillar rows are read coalesced, transposed in
-// shared memory, written as 128-byte channel rows.
+// Dense write of the three outputs, zeros included: a CTA owns 128 consecutive cells of one sample,
+// lane <-> four consecutive cells, warp <-> every 8th channel; every store is a 128-bit quad, a warp
+// writes 512 contiguous bytes of a channel row.  The (rare) pillar rows are gathered straight from
+// point_features: no staging, no barrier.  Needs cells % 4 == 0 (else the scalar kernel below).
+__global__ void __launch_bounds__(256)
+    k_radar_write4(RadarParams p, const float *__restrict__ point_features, const float *__restrict__ rcs,
+                   const int *__restrict__ pillar_at, const int *__restrict__ last_cover,
+                   const int *__restrict__ heat_bits, float *__restrict__ features,
+                   float *__restrict__ heatmap, float *__restrict__ heatmap_feat) {
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int tiles_per_sample = ceil_div(p.cells, 128);
+  const int b = blockIdx.x / tiles_per_sample;
+  const int cell = (blockIdx.x - b * tiles_per_sample) * 128 + lane * 4;
+  if (cell >= p.cells) return;
+  const size_t g = (size_t)b * p.cells + cell;
+  const int4 own = *reinterpret_cast<const int4 *>(pillar_at + g);  // (stored + 1: 0 = no pillar)
+  if (warp == 0) {
+    const int4 hb = *reinterpret_cast<const int4 *>(heat_bits + g);
+    st_stream_f4(reinterpret_cast<float4 *>(heatmap + g),
+                 make_float4(__int_as_float(hb.x), __int_as_float(hb.y), __int_as_float(hb.z), __int_as_float(hb.w)));
+  } else if (warp == 1) {
+    const int4 lc = *reinterpret_cast<const int4 *>(last_cover + g);
+    const int col = p.rcs_dim - 2;
+    float4 v;
+    v.x = lc.x > 0 ? __ldg(rcs + (size_t)(lc.x - 1) * p.rcs_dim + col) : 0.f;
+    v.y = lc.y > 0 ? __ldg(rcs + (size_t)(lc.y - 1) * p.rcs_dim + col) : 0.f;
+    v.z = lc.z > 0 ? __ldg(rcs + (size_t)(lc.z - 1) * p.rcs_dim + col) : 0.f;
+    v.w = lc.w > 0 ? __ldg(rcs + (size_t)(lc.w - 1) * p.rcs_dim + col) : 0.f;
+    st_stream_f4(reinterpret_cast<float4 *>(heatmap_feat + g), v);
+  }
+  float *dst = features + (size_t)b * p.Cin * p.cells + cell;
+  const bool any = (own.x | own.y | own.z | own.w) != 0;
+  for (int c = warp; c < p.Cin; c += 8) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (any) {
+      if (own.x > 0) v.x = __ldg(point_features + (size_t)(own.x - 1) * p.Cin + c);
+      if (own.y > 0) v.y = __ldg(point_features + (size_t)(own.y - 1) * p.Cin + c);
+      if (own.z > 0) v.z = __ldg(point_features + (size_t)(own.z - 1) * p.Cin + c);
+      if (own.w > 0) v.w = __ldg(point_features + (size_t)(own.w - 1) * p.Cin + c);
+    }
+    st_stream_f4(reinterpret_cast<float4 *>(dst + (size_t)c * p.cells), v);
+  }
+}
+
+// Scalar variant (cells % 4 != 0): 32 consecutive cells x all channels per CTA; pillar rows are
+// read coalesced, transposed in shared memory, written as 128-byte channel rows.
 __global__ void __launch_bounds__(256)
     k_radar_write(RadarParams p, const float *__restrict__ point_features, const float *__restrict__ rcs,
                   const int *__restrict__ pillar_at, const int *__restrict__ last_cover,
@@ -80,9 +186,9 @@ __global__ void __launch_bounds__(256)
     int o = -1;
     if (threadIdx.x < n) {
       const int g = b * p.cells + cell0 + threadIdx.x;
-      o = pillar_at[g];
+      o = pillar_at[g] - 1;  // (stored + 1: 0 = no pillar)
       heatmap[g] = __int_as_float(heat_bits[g]);
-      const int lc = last_cover[g];
+      const int lc = last_cover[g] - 1;
       heatmap_feat[g] = lc >= 0 ? __ldg(rcs + (size_t)lc * p.rcs_dim + p.rcs_dim - 2) : 0.f;
     }
     s_owner[threadIdx.x] = o;
@@ -149,13 +255,18 @@ extern "C" int rcb_radar_rcs_scatter(const rcb_radar_desc *d, const float *point
   cudaStream_t s = (cudaStream_t)stream;
   char *ws = static_cast<char *>(workspace);
   int *pillar_at = (int *)ws, *last_cover = (int *)(ws + plane), *heat_bits = (int *)(ws + 2 * plane);
-  RCB_CUDA_TRY(cudaMemsetAsync(ws, 0xff, 2 * plane, s));
-  RCB_CUDA_TRY(cudaMemsetAsync(heat_bits, 0, plane, s));
+  RCB_CUDA_TRY(cudaMemsetAsync(ws, 0, 3 * plane, s));  // indices are stored + 1, heat as bit patterns: 0 = nothing
   const int sms = sm_count_cached(device);
   if (p.V > 0) {
-    k_radar_splat<<<max(1, min(ceil_div(p.V, 8), sms * 32)), 256, 0, s>>>(p, rcs, coors, pillar_at,
-                                                                          last_cover, heat_bits);
+    k_radar_splat<<<max(1, min(ceil_div(p.V, kSplatPillars), sms * 16)), 256, 0, s>>>(p, rcs, coors, pillar_at,
+                                                                                     last_cover, heat_bits);
     RCB_LAUNCH_CHECK();
+  }
+  if (p.cells % 4 == 0 && (((uintptr_t)features | (uintptr_t)heatmap | (uintptr_t)heatmap_feat | (uintptr_t)workspace) % 16) == 0) {
+    k_radar_write4<<<p.B * ceil_div(p.cells, 128), 256, 0, s>>>(p, point_features, rcs, pillar_at, last_cover, heat_bits,
+                                                                features, heatmap, heatmap_feat);
+    RCB_LAUNCH_CHECK();
+    return RCB_OK;
   }
   const size_t smem = (size_t)p.Cin * 33 * 4;
   if (smem > 200 * 1024) return RCB_ERR_UNSUPPORTED;
