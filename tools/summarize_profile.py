@@ -60,10 +60,9 @@ with open(os.path.join(out_dir, f"{tag}_ncu_kernels.md"), "w") as f:
     f.write("\n".join(lines) + "\n")
 
 # DRAM traffic per launch, grouped by bench.py stage
-# bench.py's roofline is quoted on ONE kernel: "fwd" = k_pool_fwd_tile, "bwd" = k_pool_bwd_pixels16
-stage_of = {"k_cells_hist": "prepare", "k_scan_u32": "prepare", "k_radix_scatter": "prepare",
-            "k_radix_hist": "prepare", "k_cell_bounds": "prepare", "k_intervals": "prepare", "k_pool_fwd_tile": "fwd",
-            "k_pool_bwd_pixels16": "bwd", "k_pool_bwd_pixels": "bwd"}
+# bench.py's roofline is quoted on ONE kernel: "fwd" = k_fwd_cells, "bwd" = k_pool_bwd_pixels16
+stage_of = {"k_cells": "prepare", "k_tile_scatter": "prepare", "k_bucket_sort": "prepare", "k_intervals": "prepare",
+            "k_fwd_cells": "fwd", "k_pool_bwd_pixels16": "bwd", "k_pool_bwd_pixels": "bwd"}
 traffic = {}
 per_kernel = {}
 for name, d in seen.items():
@@ -77,6 +76,9 @@ for name, d in seen.items():
     if st:
         traffic[st] = traffic.get(st, 0) + int(b)
 traffic["_per_kernel"] = per_kernel
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402  (the digest bench.py compares against: a capture of other sources is reported as null)
+traffic["csrc_sha256_16"] = bench._kernel_sources_digest()
 traffic["_source"] = f"profiles/{tag}_ncu_kernels.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
 with open(os.path.join(out_dir, "traffic.json"), "w") as f:
     json.dump(traffic, f, indent=1)
@@ -96,7 +98,7 @@ if os.path.exists(src):
         f.write("\n".join(out) + "\n")
     s = sum(tot.values())
     with open(os.path.join(out_dir, f"{tag}_launch_shares.md"), "w") as f:
-        f.write(f"# kernel shares of the step, tag {tag} (ncu gpu__time_duration.sum, 40 launches)\n\n| kernel | total us | share |\n|---|---|---|\n")
+        f.write(f"# kernel shares of the step, tag {tag} (ncu gpu__time_duration.sum, --cache-control none: caches as in the un-profiled run)\n\n| kernel | total us | share |\n|---|---|---|\n")
         for n, v in sorted(tot.items(), key=lambda x: -x[1]):
             f.write(f"| {n} | {v:.1f} | {100 * v / s:.1f}% |\n")
 print(open(os.path.join(out_dir, f"{tag}_launch_shares.md")).read())
