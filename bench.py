@@ -126,6 +126,25 @@ class ClockSampler:
                 "sm_mhz_pre_spin": statistics.median(self.samples[:n_spin]) if n_spin else None}
 
 
+def pin_to_gpu_numa_node(torch, local_rank):
+    """Run this rank (and therefore the first-touch placement of its pinned staging buffers) on the CPUs
+    NVML reports as local to its GPU.  On a single-socket box this is a no-op; the record says which."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"gpu_local_cpus": len(cpus), "pinned_to": len(allowed) or len(os.sched_getaffinity(0)),
+                "host_cpus": os.cpu_count()}
+    except Exception as e:  # pragma: no cover
+        return {"error": repr(e)}
+
+
 # --------------------------------------------------------------------------------------------
 # workload
 # --------------------------------------------------------------------------------------------
@@ -176,6 +195,7 @@ def run_ours(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    affinity = pin_to_gpu_numa_node(torch, local_rank)
     lib = _lib.lib()
     B, C = WORKLOAD["batch_per_gpu"], WORKLOAD["C"]
     lo, iv, sz = rig.grid_tensors(rig.R50_GRID)
@@ -418,6 +438,7 @@ def run_ours(args):
                               "step: every step's working set exceeds the 126 MB L2",
                            kept_points=K_pts, intervals=I_iv),
             "clocks": clk,
+            "host_affinity": affinity,
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "h2d_gbs_per_rank": round(h2d * e2e_steps / (e2e_ms * 1e-3) / 1e9, 2),

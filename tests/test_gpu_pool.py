@@ -336,3 +336,55 @@ def test_hires_full_size_properties():
     # fp32 accumulation inside a cell: the error is relative to the sum of magnitudes, not to the
     # (heavily cancelling) signed total
     assert bool(((o1.double().sum(dim=(0, 2, 3, 4)) - total).abs() <= 1e-6 * scale).all())
+
+
+@pytest.mark.parametrize("grid_xyz,C,dtype,layout", [
+    ((50, 37, 2), 80, torch.float32, "bczyx"),     # patches clipped in x and in the folded (Z*Y) rows, Z = 2
+    ((50, 37, 2), 80, torch.float32, "cells_c"),   # channels-last output: rows straight out, empty cells zero-filled
+    ((13, 9, 1), 16, torch.float32, "bczyx"),      # fewer cells than one row of patches, 4 lanes carry a row
+    ((64, 64, 1), 48, torch.float32, "bczyx"),     # lane count known only at run time
+    ((64, 40, 1), 128, torch.float32, "cells_c"),  # all 32 lanes carry the row
+    ((40, 64, 1), 256, torch.float32, "bczyx"),    # two quads per lane
+    ((33, 33, 3), 136, torch.bfloat16, "bczyx"),   # two quads per lane at run time, bf16 rows
+    ((128, 128, 1), 64, torch.float16, "cells_c"),
+])
+def test_forward_cells_kernel_variants(grid_xyz, C, dtype, layout):
+    """k_fwd_cells over its template / layout space on ragged synthetic points: a few cells hold
+    hundreds of points (several 32-point chunks, merged runs of one pixel), most hold a handful, many
+    are empty; grids that are not multiples of the 8 x 4 patch."""
+    import rcbevdet_b200 as rcb
+    gx, gy, gz = grid_xyz
+    B, N, D, H, W = 2, 2, 24, 6, 10
+    rng = np.random.default_rng(gx * 1000 + C)
+    coor = np.empty((B, N, D, H, W, 3), np.float32)
+    coor[..., 0] = rng.random((B, N, D, H, W), dtype=np.float32) * (gx + 6) - 3
+    coor[..., 1] = rng.random((B, N, D, H, W), dtype=np.float32) * (gy + 6) - 3
+    coor[..., 2] = rng.random((B, N, D, H, W), dtype=np.float32) * (gz + 1) - 0.5
+    # one camera's whole frustum into a 2 x 2 block of cells: long cells with every depth bin of a pixel
+    # in one cell (runs of D equal rows to merge, in groups of four)
+    coor[0, 0, ..., 0] = gx // 2 + rng.random((D, H, W), dtype=np.float32) * 2 - 1
+    coor[0, 0, ..., 1] = gy // 2 + rng.random((D, H, W), dtype=np.float32) * 2 - 1
+    coor[0, 0, ..., 0] = np.floor(coor[0, 0, :1, ..., 0]) + 0.5            # same (x, y) for all bins of a pixel
+    coor[0, 0, ..., 1] = np.floor(coor[0, 0, :1, ..., 1]) + 0.5
+    coor[0, 0, ..., 2] = 0.25
+    lo, iv, sz = np.float32([0, 0, 0]), np.float32([1, 1, 1]), np.float32([gx, gy, gz])
+    depth = rng.random((B, N, D, H, W), dtype=np.float32)
+    feat = rng.standard_normal((B, N, C, H, W), dtype=np.float32)
+    feat_t = torch.from_numpy(feat).to(dtype)
+    rows = feat_t.float().permute(0, 1, 3, 4, 2).contiguous().numpy()      # what the kernel sees after rounding
+    ranks = oracle.voxel_pooling_prepare_v2(coor, lo, iv, sz)
+    shape = (B, gz, gy, gx, C)
+    want = oracle.bev_pool_v2_forward(depth, rows, ranks[1], ranks[2], ranks[0], shape, ranks[3], ranks[4], threads=8)
+    assert int(ranks[4].max()) > 100 and (want.reshape(-1, C) == 0).all(1).any()   # long cells and empty cells
+    rb, rd, rf, st, ln = rcb.voxel_pooling_prepare_v2(torch.from_numpy(coor).cuda(), lo, iv, sz)
+    fview = feat_t.cuda().permute(0, 1, 3, 4, 2)
+    tol = RTOL32 if dtype == torch.float32 else 1e-4   # same rounded rows on both sides: only the summation differs
+    if layout == "bczyx":
+        got = rcb.bev_pool_v2(torch.from_numpy(depth).cuda(), fview, rd, rf, rb, shape, st, ln)
+        _close(got, oracle.to_bczyx(want), tol, "bev (B,C,Z,Y,X)")
+    else:
+        got = rcb.QuickCumsumCuda.apply(torch.from_numpy(depth).cuda(), fview, rd, rf, rb, shape, st, ln)
+        _close(got, want, tol, "bev (B,Z,Y,X,C)")
+    empty = (want.reshape(-1, C) == 0).all(1)
+    got_rows = (got.permute(0, 2, 3, 4, 1) if layout == "bczyx" else got).reshape(-1, C)
+    assert float(got_rows[torch.from_numpy(empty).cuda()].abs().max()) == 0.0      # untouched cells are exactly zero
