@@ -50,6 +50,9 @@ __global__ void __launch_bounds__(256) k_planes_to_rows(const TIn *__restrict__ 
 // above spends ~36 instructions per element on index arithmetic and is issue-bound (ncu: 75 %
 // issue-active at 3.2 TB/s); this one moves four elements per load/store instruction.
 constexpr int kV4Pixels = 64;
+#ifndef RCB_V4_MIN_HW
+#define RCB_V4_MIN_HW 256
+#endif
 __global__ void __launch_bounds__(256) k_planes_to_rows_v4(const float *__restrict__ src, float *__restrict__ dst,
                                                            int C, int HW, long long src_img_stride) {
   pdl_prologue();
@@ -60,11 +63,29 @@ __global__ void __launch_bounds__(256) k_planes_to_rows_v4(const float *__restri
   const int n_hw = min(kV4Pixels, HW - hw0);  // multiple of 4
   const float *s = src + (size_t)img * src_img_stride + hw0;
   const int quads_per_row = n_hw >> 2;
-  for (int f = threadIdx.x; f < C * quads_per_row; f += 256) {
-    const int c = f / quads_per_row, j = f - c * quads_per_row;
-    const float4 v = ld_stream_f4(reinterpret_cast<const float4 *>(s + (size_t)c * HW) + j);
-    float *t = tile_v4 + (4 * j) * P + c;
-    t[0] = v.x, t[P] = v.y, t[2 * P] = v.z, t[3 * P] = v.w;
+  // five 128-bit loads in flight per thread before the first shared-memory store (C = 80: the whole
+  // tile in one trip); left as a plain loop the compiler keeps one load per trip in flight
+  constexpr int kBatch = 5;
+  const int n_f = C * quads_per_row;
+  for (int f0 = threadIdx.x; f0 < n_f; f0 += 256 * kBatch) {
+    float4 v[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int f = f0 + 256 * u;
+      if (f < n_f) {
+        const int c = f / quads_per_row, j = f - c * quads_per_row;
+        v[u] = ld_stream_f4(reinterpret_cast<const float4 *>(s + (size_t)c * HW) + j);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int f = f0 + 256 * u;
+      if (f < n_f) {
+        const int c = f / quads_per_row, j = f - c * quads_per_row;
+        float *t = tile_v4 + (4 * j) * P + c;
+        t[0] = v[u].x, t[P] = v[u].y, t[2 * P] = v[u].z, t[3 * P] = v[u].w;
+      }
+    }
   }
   __syncthreads();
   float4 *d = reinterpret_cast<float4 *>(dst + ((size_t)img * HW + hw0) * C);
@@ -80,7 +101,7 @@ int planes_to_rows_launch(const void *src, void *dst, int n_img, int C, int HW,
                           long long src_img_stride, int elem_bytes, cudaStream_t s) {
   if (n_img <= 0 || C <= 0 || HW <= 0) return RCB_OK;
   if (n_img > 65535) return RCB_ERR_UNSUPPORTED;
-  if (elem_bytes == 4 && (C % 4) == 0 && (HW % 4) == 0 && HW >= 2048 && C <= 256 && (src_img_stride % 4) == 0 &&
+  if (elem_bytes == 4 && (C % 4) == 0 && (HW % 4) == 0 && HW >= RCB_V4_MIN_HW && C <= 256 && (src_img_stride % 4) == 0 &&
       (((uintptr_t)src) % 16) == 0 && (((uintptr_t)dst) % 16) == 0) {
     const size_t smem = (size_t)kV4Pixels * (C + 1) * 4;
     if (smem > 48 * 1024)
