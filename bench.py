@@ -206,7 +206,9 @@ def run_ours(args):
     n_kernels = {"prepare": 5, "feat_rows": 1, "fwd": 1, "og_rows": 1, "bwd": 1}
     stage_events = {s: [] for s in stage_names}
 
-    def step(i, record):
+    og_rows_cl = [None] * N_SETS   # out_grad of each set as channels-last rows (the channels-last variant's input)
+
+    def step(i, record, channels_last=False):
         coor, depth, feat, out_grad = sets[i % N_SETS]
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)] if record else None
         if record:
@@ -221,16 +223,20 @@ def run_ours(args):
         d.n_points, d.n_intervals, d.C = prepared.P, 0, C
         d.B, d.Z, d.Y, d.X = B, 1, 128, 128
         d.n_depth, d.n_pixels, d.D, d.HW, d.H = depth.numel(), rows.shape[0], prepared.D, prepared.HW, prepared.H
-        d.layout, d.feat_dtype, d.flags = _lib.LAYOUT_B_C_CELLS, _lib.DTYPE_F32, _lib.PLAN_ALL
-        out = torch.empty((B, C, 1, 128, 128), dtype=torch.float32, device=dev)
+        d.layout = _lib.LAYOUT_CELLS_C if channels_last else _lib.LAYOUT_B_C_CELLS
+        d.feat_dtype, d.flags = _lib.DTYPE_F32, _lib.PLAN_ALL
+        out = torch.empty((B, 1, 128, 128, C) if channels_last else (B, C, 1, 128, 128), dtype=torch.float32, device=dev)
         bp.pool_forward(d, depth, rows, prepared.ranks_depth, prepared.ranks_feat, prepared.ranks_bev, None, None,
                         prepared.cell_start, out)                                                  # row F
         if record:
             ev[3].record(stream)
         # backward = out_grad (B,C,cells) -> channels-last rows (bev_pool.py:69), then the gradient kernel
-        og_rows = torch.empty((B * 128 * 128, C), dtype=torch.float32, device=dev)
-        _lib.check(lib.rcb_planes_to_rows(_lib.ptr(out_grad), _lib.ptr(og_rows), B, C, 128 * 128, C * 128 * 128, 4,
-                                          dev.index, _lib.stream_ptr(dev)), "og_rows")
+        if channels_last:   # the gradient arrives channels-last (bev_pool_v2(..., channels_last=True)): used in place
+            og_rows = og_rows_cl[i % N_SETS]
+        else:
+            og_rows = torch.empty((B * 128 * 128, C), dtype=torch.float32, device=dev)
+            _lib.check(lib.rcb_planes_to_rows(_lib.ptr(out_grad), _lib.ptr(og_rows), B, C, 128 * 128, C * 128 * 128, 4,
+                                              dev.index, _lib.stream_ptr(dev)), "og_rows")
         if record:
             ev[4].record(stream)
         depth_grad = torch.empty_like(depth)
@@ -312,10 +318,27 @@ def run_ours(args):
 
     variants = None
     if not args.profile:
+        # the opt-in channels-last result (no transposed write, gradient consumed in place): same step,
+        # out_grad resident as channels-last rows -- what a BEV encoder in torch.channels_last hands back
+        for k in range(N_SETS):
+            og_rows_cl[k] = sets[k][3].view(B, C, 128 * 128).permute(0, 2, 1).contiguous().view(B * 128 * 128, C)
+        n_cl = max(20, min(args.steps, 200))
+        for i in range(10):
+            step(i, False, channels_last=True)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for i in range(n_cl):
+            step(i, False, channels_last=True)
+        c1.record(stream)
+        torch.cuda.synchronize(dev)
+        step_cl_ms = c0.elapsed_time(c1) / n_cl
         rows32 = bp.feat_rows(sets[0][2].permute(0, 1, 3, 4, 2))
         variants = {"fwd_f32_rows_ms": round(fwd_only(rows32, _lib.DTYPE_F32), 5),
                     "fwd_bf16_rows_ms": round(fwd_only(rows32.bfloat16(), _lib.DTYPE_BF16), 5),
-                    "note": "forward kernel alone, same plan, 4 rotating outputs (inputs L2-warm)"}
+                    "step_channels_last_ms": round(step_cl_ms, 5),
+                    "note": "fwd_*: forward kernel alone, same plan, 4 rotating outputs (inputs L2-warm); "
+                            "step_channels_last_ms: the whole step with bev_pool_v2(..., channels_last=True) "
+                            "semantics (rows written directly, channels-last out_grad used in place)"}
 
     # ---- end to end through the public API from pinned host buffers --------------------------
     from rcbevdet_b200.prepare import frustum_axes, pack_calib

@@ -116,10 +116,27 @@ def _forward(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, in
     return out, saved, desc, plan
 
 
-def _backward(out_grad, saved, desc, plan, feat_shape, feat_dtype, depth_shape, depth_dtype):
+def _backward(out_grad, saved, desc, plan, feat_shape, feat_dtype, depth_shape, depth_dtype, logical_bczyx=None):
+    """`logical_bczyx`: out_grad has the shape (B, C, Z, Y, X) (what bev_pool_v2 returns) rather than
+    (B, Z, Y, X, C); None = what desc.layout says.  Its MEMORY decides which kernel path runs: a
+    gradient that is channels-last in memory (the forward was asked for `channels_last`, or the
+    consumer runs in torch.channels_last) is used in place as rows; a (B, C, cells)-contiguous one goes
+    through the transpose kernel, as the reference's out_grad.contiguous() does (bev_pool.py:69)."""
     depth, rows, ranks_depth, ranks_feat, ranks_bev = saved
     dev = depth.device
-    out_grad = out_grad.contiguous().float()             # bev_pool.py:69
+    if logical_bczyx is None:
+        logical_bczyx = desc.layout == _lib.LAYOUT_B_C_CELLS
+    out_grad = out_grad.float()
+    bwd_desc = _lib.PoolDesc.from_buffer_copy(desc)      # the forward's descriptor is shared with the caller
+    if not logical_bczyx:
+        out_grad = out_grad.contiguous()                 # bev_pool.py:69
+        bwd_desc.layout = _lib.LAYOUT_CELLS_C
+    elif out_grad.dim() == 5 and not out_grad.is_contiguous() and out_grad.permute(0, 2, 3, 4, 1).is_contiguous():
+        bwd_desc.layout = _lib.LAYOUT_CELLS_C            # rows in place: no transpose pass
+    else:
+        out_grad = out_grad.contiguous()
+        bwd_desc.layout = _lib.LAYOUT_B_C_CELLS
+    desc = bwd_desc
     depth_grad = torch.empty(depth.shape, dtype=torch.float32, device=dev)
     feat_grad = torch.empty(rows.shape, dtype=torch.float32, device=dev)
     lib = _lib.lib()
@@ -153,9 +170,10 @@ class _PoolFunction(torch.autograd.Function):
 
     @staticmethod
     def _bwd(ctx, out_grad):
-        desc, plan, feat_shape, feat_dtype, depth_shape, depth_dtype = ctx.rcb
+        desc, plan, feat_shape, feat_dtype, depth_shape, depth_dtype = ctx.rcb[:6]
+        logical = ctx.rcb[6] if len(ctx.rcb) > 6 else None
         depth_grad, feat_grad = _backward(out_grad, ctx.saved_tensors, desc, plan, feat_shape, feat_dtype,
-                                          depth_shape, depth_dtype)
+                                          depth_shape, depth_dtype, logical)
         return depth_grad, feat_grad, None, None, None, None, None, None
 
 
@@ -192,13 +210,35 @@ class _BevPoolV2Fused(_PoolFunction):
         return _PoolFunction._bwd(ctx, out_grad)
 
 
-def bev_pool_v2(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, interval_starts,
+class _BevPoolV2ChannelsLast(_PoolFunction):
+    """bev_pool_v2 with a channels-last result: same shape (B, C, Z, Y, X), memory (B, Z, Y, X, C).
+    The forward writes rows directly and the backward takes a channels-last gradient in place: neither
+    the permute copy of bev_pool.py:91 nor its mirror image at :69 exists in any form."""
+    _layout = _lib.LAYOUT_CELLS_C
+
+    @staticmethod
+    def forward(ctx, depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, interval_starts,
                 interval_lengths):
+        out = _BevPoolV2ChannelsLast._fwd(ctx, depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape,
+                                          interval_starts, interval_lengths)
+        ctx.rcb = ctx.rcb + (True,)                      # out_grad is logically (B, C, Z, Y, X)
+        return out.permute(0, 4, 1, 2, 3)
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        return _PoolFunction._bwd(ctx, out_grad)
+
+
+def bev_pool_v2(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, interval_starts,
+                interval_lengths, channels_last=False):
     """depth (B,N,D,H,W); feat (B,N,H,W,C) (any strides); ranks/intervals as produced by
     voxel_pooling_prepare_v2; bev_feat_shape = (B,Z,Y,X,C).  Returns (B,C,Z,Y,X) contiguous float32
-    (bev_pool.py:86-92)."""
-    return _BevPoolV2Fused.apply(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape,
-                                 interval_starts, interval_lengths)
+    (bev_pool.py:86-92).  channels_last=True (an extension; the reference has no such mode): the same
+    shape with channels-last memory -- no transposed write, and a channels-last gradient is consumed
+    in place by the backward (a BEV encoder run in torch.channels_last produces one)."""
+    fn = _BevPoolV2ChannelsLast if channels_last else _BevPoolV2Fused
+    return fn.apply(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, interval_starts,
+                    interval_lengths)
 
 
 class TRTBEVPoolv2(torch.autograd.Function):

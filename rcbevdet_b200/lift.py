@@ -74,14 +74,15 @@ def depth_context_split(x, D, C):
     return _DepthContextSplit.apply(x, int(D), int(C))
 
 
-def lss_view_transform(x, n_cams, D, C, calib, axes, grid_lower_bound, grid_interval, grid_size, collapse_z=True):
+def lss_view_transform(x, n_cams, D, C, calib, axes, grid_lower_bound, grid_interval, grid_size, collapse_z=True,
+                       channels_last=False):
     """LSSViewTransformer.forward from the depth-net output on (view_transformer.py:316-320 +
     view_transform_core's non-accelerated branch :290-294) as one device-side chain:
     x (B*N, D + C, H, W); calib = get_lidar_coor's six tensors (or a packed pair from pack_calib);
     axes = frustum_axes(...).  Returns (bev_feat, depth) like the reference: bev_feat (B, C*Z, Y, X)
     (collapse_z) and depth (B*N, D, H, W)."""
     from .prepare import prepare_from_calib_async
-    from .view_pool import _ViewPool, fused_path_supports
+    from .view_pool import _ViewPool, _collapse_z, fused_path_supports
     if not fused_path_supports(C):
         raise ValueError(f"lss_view_transform needs C % 4 == 0 (C % 8 above 128 channels, C <= 256), got {C}")
     bn, _, H, W = x.shape
@@ -90,7 +91,7 @@ def lss_view_transform(x, n_cams, D, C, calib, axes, grid_lower_bound, grid_inte
     B = bn // n_cams
     depth, ctx_cl = depth_context_split(x, D, C)
     prepared = prepare_from_calib_async(calib, axes, grid_lower_bound, grid_interval, grid_size, device=x.device)
-    bev = _ViewPool.apply(depth.view(B, n_cams, D, H, W), ctx_cl.view(B, n_cams, H, W, C), prepared)
+    bev = _ViewPool.apply(depth.view(B, n_cams, D, H, W), ctx_cl.view(B, n_cams, H, W, C), prepared, channels_last)
     if collapse_z:
-        bev = torch.cat(bev.unbind(dim=2), 1)
+        bev = _collapse_z(bev)
     return bev, depth

@@ -19,7 +19,7 @@ from .prepare import prepare_async, prepare_from_calib_async
 
 class _ViewPool(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, depth, feat, prepared):
+    def forward(ctx, depth, feat, prepared, channels_last=False):
         dev = depth.device
         depth_c = depth.detach().contiguous().float()
         rows = _bp.feat_rows(feat.detach())
@@ -30,24 +30,32 @@ class _ViewPool(torch.autograd.Function):
         d.B, d.Z, d.Y, d.X = prepared.B, gz, gy, gx
         d.n_depth, d.n_pixels = depth_c.numel(), rows.shape[0]
         d.D, d.HW, d.H = prepared.D, prepared.HW, prepared.H
-        d.layout, d.feat_dtype, d.flags = _lib.LAYOUT_B_C_CELLS, _bp._DTYPES[rows.dtype], _lib.PLAN_ALL
+        d.layout = _lib.LAYOUT_CELLS_C if channels_last else _lib.LAYOUT_B_C_CELLS
+        d.feat_dtype, d.flags = _bp._DTYPES[rows.dtype], _lib.PLAN_ALL
         if d.n_depth != prepared.P or d.n_pixels * d.D != d.n_depth:
             raise ValueError("depth / feat shapes do not match the frustum that `coor` describes")
-        out = torch.empty((prepared.B, C, gz, gy, gx), dtype=torch.float32, device=dev)
+        shape = (prepared.B, gz, gy, gx, C) if channels_last else (prepared.B, C, gz, gy, gx)
+        out = torch.empty(shape, dtype=torch.float32, device=dev)
         _bp.pool_forward(d, depth_c, rows, prepared.ranks_depth, prepared.ranks_feat, prepared.ranks_bev, None, None,
                          prepared.cell_start, out)
         ctx.save_for_backward(depth_c, rows, prepared.ranks_depth, prepared.ranks_feat, prepared.ranks_bev)
         plan = _plan.PoolPlan(_lib.PLAN_ALL, prepared.cell_start, prepared.point_cell, prepared.D,
                               prepared.HW, prepared.n_cells, prepared.P)
         ctx.rcb = (d, plan, tuple(feat.shape), feat.dtype, tuple(depth.shape), depth.dtype)
-        return out
+        return out.permute(0, 4, 1, 2, 3) if channels_last else out   # logically (B, C, Z, Y, X) either way
 
     @staticmethod
     def backward(ctx, out_grad):
         desc, plan, feat_shape, feat_dtype, depth_shape, depth_dtype = ctx.rcb
         depth_grad, feat_grad = _bp._backward(out_grad, ctx.saved_tensors, desc, plan, feat_shape,
-                                              feat_dtype, depth_shape, depth_dtype)
-        return depth_grad, feat_grad, None
+                                              feat_dtype, depth_shape, depth_dtype, True)
+        return depth_grad, feat_grad, None, None
+
+
+def _collapse_z(bev):
+    """view_transformer.py:203-204: (B, C, Z, Y, X) -> (B, C*Z, Y, X).  Z == 1 is a view (it keeps a
+    channels-last result channels-last); the general case concatenates like the reference."""
+    return bev.squeeze(2) if bev.shape[2] == 1 else torch.cat(bev.unbind(dim=2), 1)
 
 
 def fused_path_supports(C):
@@ -59,7 +67,7 @@ def fused_path_supports(C):
 
 
 def voxel_pooling_v2(coor, depth, feat, grid_lower_bound, grid_interval, grid_size, collapse_z=True,
-                     return_prepared=False):
+                     return_prepared=False, channels_last=False):
     """coor (B,N,D,H,W,3) fp32; depth (B,N,D,H,W); feat (B,N,C,H,W) -- exactly the arguments of
     the reference method.  Returns bev_feat (B, C*Z, Y, X) (collapse_z) or (B,C,Z,Y,X)."""
     C = int(feat.shape[2])
@@ -81,14 +89,14 @@ def voxel_pooling_v2(coor, depth, feat, grid_lower_bound, grid_interval, grid_si
         return torch.cat(bev.unbind(dim=2), 1) if collapse_z else bev
     prepared = prepare_async(coor, grid_lower_bound, grid_interval, grid_size)
     feat = feat.permute(0, 1, 3, 4, 2)                       # view_transformer.py:195
-    bev = _ViewPool.apply(depth, feat, prepared)
+    bev = _ViewPool.apply(depth, feat, prepared, channels_last)
     if collapse_z:
-        bev = torch.cat(bev.unbind(dim=2), 1)                # view_transformer.py:203-204
+        bev = _collapse_z(bev)                               # view_transformer.py:203-204
     return (bev, prepared) if return_prepared else bev
 
 
 def voxel_pooling_v2_from_calib(calib, axes, depth, feat, grid_lower_bound, grid_interval, grid_size,
-                                collapse_z=True, return_prepared=False):
+                                collapse_z=True, return_prepared=False, channels_last=False):
     """get_lidar_coor + voxel_pooling_v2 (view_transformer.py:290-294) as one device-side chain:
     `calib` = (sensor2ego, ego2global, cam2imgs, post_rots, post_trans, bda) or a packed (cam, bda)
     pair, `axes` = frustum_axes(...); depth (B,N,D,H,W); feat (B,N,C,H,W).  The frustum points
@@ -107,7 +115,7 @@ def voxel_pooling_v2_from_calib(calib, axes, depth, feat, grid_lower_bound, grid
         else:
             bev = _bp.bev_pool_v2(depth, feat.permute(0, 1, 3, 4, 2), rd, rf, rb, (prepared.B, gz, gy, gx, C), st, ln)
         return torch.cat(bev.unbind(dim=2), 1) if collapse_z else bev
-    bev = _ViewPool.apply(depth, feat.permute(0, 1, 3, 4, 2), prepared)
+    bev = _ViewPool.apply(depth, feat.permute(0, 1, 3, 4, 2), prepared, channels_last)
     if collapse_z:
-        bev = torch.cat(bev.unbind(dim=2), 1)
+        bev = _collapse_z(bev)
     return (bev, prepared) if return_prepared else bev

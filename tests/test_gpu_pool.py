@@ -388,3 +388,48 @@ def test_forward_cells_kernel_variants(grid_xyz, C, dtype, layout):
     empty = (want.reshape(-1, C) == 0).all(1)
     got_rows = (got.permute(0, 2, 3, 4, 1) if layout == "bczyx" else got).reshape(-1, C)
     assert float(got_rows[torch.from_numpy(empty).cuda()].abs().max()) == 0.0      # untouched cells are exactly zero
+
+
+def test_channels_last_result_and_gradient_in_place():
+    """bev_pool_v2(..., channels_last=True) / voxel_pooling_v2(..., channels_last=True): same shape and
+    values as the reference layout, channels-last memory, and the backward agrees whether the incoming
+    gradient is channels-last (used in place as rows) or (B, C, cells)-contiguous (transposed first)."""
+    import rcbevdet_b200 as rcb
+    from rcbevdet_b200 import rig
+    grid = rig.R50_GRID
+    coor, depth, feat = _case(B=2, seed=31)
+    lo, iv, sz = rig.grid_tensors(grid)
+    rb, rd, rf, st, ln = rcb.voxel_pooling_prepare_v2(coor.cuda(), lo, iv, sz)
+    shape = (2, 1, 128, 128, 80)
+    og = torch.randn(2, 80, 1, 128, 128, device="cuda", generator=torch.Generator("cuda").manual_seed(4))
+    results = {}
+    for mode in ("ref", "cl", "cl_grad_contig"):
+        d = depth.cuda().requires_grad_(True)
+        f = feat.cuda().requires_grad_(True)
+        bev = rcb.bev_pool_v2(d, f.permute(0, 1, 3, 4, 2), rd, rf, rb, shape, st, ln, channels_last=mode != "ref")
+        assert bev.shape == (2, 80, 1, 128, 128)
+        if mode == "ref":
+            assert bev.is_contiguous()
+            bev.backward(og)
+        else:
+            assert bev.permute(0, 2, 3, 4, 1).is_contiguous() and not bev.is_contiguous()
+            g = og if mode == "cl_grad_contig" else og.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
+            bev.backward(g)
+        results[mode] = (bev.detach().contiguous(), d.grad, f.grad)
+    for mode in ("cl", "cl_grad_contig"):
+        for a, b, what in zip(results[mode], results["ref"], ("bev", "depth_grad", "feat_grad")):
+            assert float((a - b).abs().max()) <= 1e-6 * float(b.abs().max()), f"{mode}: {what}"
+    # the fused chain, Z == 1: (B, C, Y, X) channels-last, i.e. torch.channels_last
+    d = depth.cuda().requires_grad_(True)
+    f = feat.cuda().requires_grad_(True)
+    bev = rcb.voxel_pooling_v2(coor.cuda(), d, f, lo, iv, sz, channels_last=True)
+    assert bev.shape == (2, 80, 128, 128) and bev.is_contiguous(memory_format=torch.channels_last)
+    ref = rcb.voxel_pooling_v2(coor.cuda(), depth.cuda(), feat.cuda(), lo, iv, sz)
+    assert float((bev - ref).abs().max()) <= 1e-6 * float(ref.abs().max())
+    conv = torch.nn.Conv2d(80, 8, 3, padding=1).cuda().to(memory_format=torch.channels_last)
+    conv(bev).square().mean().backward()
+    d2 = depth.cuda().requires_grad_(True)
+    f2 = feat.cuda().requires_grad_(True)
+    conv(rcb.voxel_pooling_v2(coor.cuda(), d2, f2, lo, iv, sz)).square().mean().backward()
+    assert float((d.grad - d2.grad).abs().max()) <= 1e-4 * float(d2.grad.abs().max())
+    assert float((f.grad - f2.grad).abs().max()) <= 1e-4 * float(f2.grad.abs().max())
