@@ -104,11 +104,15 @@ def test_long_cells_every_sort_tier(n_cells_hit, P):
     ((100, 50, 3), 2, 120000, 0.3),     # 30000 cells, not a power of two, Z > 1
     ((128, 128, 1), 3, 200000, 0.7),    # R50 grid, 140k points in one row of one sample
     ((1024, 1024, 1), 1, 150000, 0.2),  # 2^20 cells: 1024-cell buckets
-    ((1500, 1000, 1), 1, 100000, 0.2),  # > 2^20 cells: three plain LSD passes
+    ((1500, 1000, 1), 1, 100000, 0.2),  # 1.5 M cells: 2048-cell buckets (two-level up to 2^22 cells)
+    ((2048, 2048, 1), 1, 120000, 0.3),  # exactly 2^22 cells: 4096-cell buckets, the last two-level grid
+    ((2500, 2000, 1), 1, 100000, 0.2),  # 5 M cells > 2^22: three plain LSD passes (prepare_lsd.cu)
+    ((700, 700, 1), 9, 90000, 0.0),     # 4.4 M cells in 9 samples: LSD passes with a batch offset
 ])
 def test_two_level_sort_grids(grid, B, P, hot):
-    """Every sort path of the prepare stage (one LSD pass, global pass + bucket sort with one
-    and several chunks per bucket, three LSD passes), bit-exact against the oracle."""
+    """Every sort path of the prepare stage (global pass + bucket sort with one and several chunks per
+    bucket, every bucket width up to 4096 cells, three LSD passes beyond 2^22 cells), bit-exact
+    against the oracle."""
     rng = np.random.default_rng(P + grid[0])
     gx, gy, gz = grid
     per = P // B
