@@ -593,6 +593,34 @@ def _radar_case(torch, rcb, rig, dev, B, n):
             "gbs": round(alg / (t * 1e-3) / 1e9, 1), "frac_of_hbm_peak": round(alg / (t * 1e-3) / 1e9 / peak, 4)}
 
 
+def _graph_case(torch, rcb, rig, dev):
+    """BASELINE config 1's geometry (one sample) on the GPU: the calibration-driven chain + backward, eager
+    and replayed from a CUDA graph (the chain never touches the host, so it captures as is).  One sample
+    is host-launch-bound when launched eagerly."""
+    axes = rcb.frustum_axes(rig.R50_GRID["depth"], rig.R50_INPUT, 16, device=dev)
+    cam, bda = (t.to(dev) for t in rcb.pack_calib(*rig.camera_rig(1)))
+    lo, iv, sz = rig.grid_tensors(rig.R50_GRID)
+    depth, feat = (t.to(dev) for t in rig.pooling_inputs(1, 6, 118, 16, 44, WORKLOAD["C"], seed=1))
+    og = torch.randn(1, WORKLOAD["C"], 128, 128, device=dev)
+
+    def step():
+        d_ = depth.detach().requires_grad_(True)
+        f_ = feat.detach().requires_grad_(True)
+        rcb.voxel_pooling_v2_from_calib((cam, bda), axes, d_, f_, lo, iv, sz).backward(og)
+    t_eager = _time_cuda(torch, step, n_warm=5, n=50)
+    side = torch.cuda.Stream(dev)
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        step()
+    t_graph = _time_cuda(torch, graph.replay, n_warm=5, n=50)
+    return {"eager_ms": round(t_eager, 4), "cuda_graph_ms": round(t_graph, 4),
+            "samples_per_s": round(1 / (t_graph * 1e-3), 1),
+            "note": "prepare (from calibration) + forward + backward of ONE sample; samples_per_s is the graph replay"}
+
+
 def extra_configs(torch, rcb, rig, _lib, bp, dev, lib):
     """BASELINE configs 3, 4, 5 on one GPU, each through the public device-side API
     (rcbevdet_b200.voxel_pooling_v2 / radar_rcs_scatter), 10 timed calls after 3 warm-ups."""
@@ -609,6 +637,7 @@ def extra_configs(torch, rcb, rig, _lib, bp, dev, lib):
         for b in (1, 2, 4, 8):
             out[f"hires_256_B{b}"] = _pool_case(torch, rcb, rig, dev, b, rig.HIRES_GRID, rig.HIRES_INPUT, C)
             torch.cuda.empty_cache()
+        out["r50_B1_latency"] = _graph_case(torch, rcb, rig, dev)
         # config 4: RCS-aware radar scatter, B=8, 5 sweeps x 5 radars x 125 points per sample
         out["radar_128"] = _radar_case(torch, rcb, rig, dev, 8, 128)
         out["radar_512"] = _radar_case(torch, rcb, rig, dev, 8, 512)

@@ -161,3 +161,43 @@ def test_install_fuses_view_transform_core():
     lo, iv, sz = rig.grid_tensors(rig.R50_GRID)
     want = rcb.voxel_pooling_v2(coor.cuda(), depth.cuda(), feat.cuda(), lo, iv, sz)
     assert torch.equal(bev, want)
+
+
+def test_fused_chain_is_cuda_graph_capturable():
+    """The calibration-driven chain (prepare -> pool -> backward) reads nothing back to the host and
+    allocates only through torch's allocator: it can be captured in a CUDA graph and replayed with new
+    contents in the same buffers (small batches are host-launch-bound: B = 1 runs 2.2x faster replayed)."""
+    import rcbevdet_b200 as rcb
+    from rcbevdet_b200 import rig
+    B = 1
+    axes = rcb.frustum_axes(rig.R50_GRID["depth"], rig.R50_INPUT, 16, device="cuda")
+    cam, bda = (t.cuda() for t in rcb.pack_calib(*rig.camera_rig(B)))
+    lo, iv, sz = rig.grid_tensors(rig.R50_GRID)
+    depth, feat = (t.cuda() for t in rig.pooling_inputs(B, 6, 118, 16, 44, 80, seed=1))
+    og = torch.randn(B, 80, 128, 128, device="cuda", generator=torch.Generator("cuda").manual_seed(2))
+
+    def step():
+        d = depth.detach().requires_grad_(True)
+        f = feat.detach().requires_grad_(True)
+        bev = rcb.voxel_pooling_v2_from_calib((cam, bda), axes, d, f, lo, iv, sz)
+        bev.backward(og)
+        return bev.detach(), d.grad, f.grad
+
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            step()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        captured = step()
+    # new inputs in the captured buffers: other depth / context values AND another calibration
+    depth2, feat2 = (t.cuda() for t in rig.pooling_inputs(B, 6, 118, 16, 44, 80, seed=5))
+    cam2, bda2 = (t.cuda() for t in rcb.pack_calib(*rig.camera_rig(B, aug_seed=3)))
+    depth.copy_(depth2), feat.copy_(feat2), cam.copy_(cam2), bda.copy_(bda2)
+    graph.replay()
+    torch.cuda.synchronize()
+    got = [t.clone() for t in captured]
+    want = step()
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
