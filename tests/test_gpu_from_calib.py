@@ -201,3 +201,29 @@ def test_fused_chain_is_cuda_graph_capturable():
     want = step()
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+def test_fused_chains_with_nothing_inside_the_grid():
+    """view_transformer.py:184-194: when no frustum point falls inside the grid the reference returns
+    zeros of the pooled shape.  The sync-free chains get there without knowing it (every CSR entry is
+    0, every cell is written as zero) and their backward returns zero gradients."""
+    import rcbevdet_b200 as rcb
+    from rcbevdet_b200 import rig
+    B, N, D, H, W, C = 1, 2, 5, 3, 4, 8
+    coor = torch.full((B, N, D, H, W, 3), 1000.0, device="cuda")          # everything far outside
+    lo, iv, sz = rig.grid_tensors(rig.R50_GRID)
+    depth = torch.rand(B, N, D, H, W, device="cuda", requires_grad=True)
+    feat = torch.randn(B, N, C, H, W, device="cuda", requires_grad=True)
+    assert rcb.voxel_pooling_prepare_v2(coor, lo, iv, sz) == (None,) * 5
+    for cl in (False, True):
+        bev = rcb.voxel_pooling_v2(coor, depth, feat, lo, iv, sz, channels_last=cl)
+        assert bev.shape == (B, C, 128, 128) and float(bev.detach().abs().max()) == 0.0
+        bev.sum().backward()
+        assert float(depth.grad.abs().max()) == 0.0 and float(feat.grad.abs().max()) == 0.0
+    far = list(rig.camera_rig(B))
+    far[0] = far[0].clone()
+    far[0][:, :, :3, 3] += 5000.0                                         # cameras 5 km away from the grid
+    axes = rcb.frustum_axes([1.0, 6.0, 1.0], (48, 64), 16)
+    x = torch.randn(B * 6, D + C, H, W, device="cuda")
+    bev, dep = rcb.lss_view_transform(x, 6, D, C, tuple(far), axes, lo, iv, sz)
+    assert float(bev.abs().max()) == 0.0 and dep.shape == (B * 6, D, H, W)
