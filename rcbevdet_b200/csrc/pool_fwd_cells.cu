@@ -4,10 +4,11 @@
 // mmdet3d/ops/bev_pool_v2/bev_pool.py:27,91 are folded in (every cell written once, final layout).
 //
 // k_fwd_cells: one CTA per kPatchX x kPatchY patch of BEV cells; a WARP pools one cell at a time.
-// The patch's cells are ranked by length and dealt to the warps in snake order (longest first, a
-// static LPT schedule: no queue, no atomics).  Between the opening barrier (cell bounds + order)
-// and the closing one (write-out) the warps never wait for each other: the kernel's critical path
-// is one cell (<= 656 points on the R50 grid), not one patch (6 k points).
+// The patch's cells are ranked by length and the warps take them longest first from a shared counter
+// (a static longest-first schedule, RCB_FWD_STATIC, measured 1.8x slower: a warp that runs out of work
+// idles while its CTA keeps the SM's slots).  Between the opening barrier (cell bounds + order) and
+// the closing one (write-out) the warps never wait for each other: the kernel's critical path is one
+// cell (<= 656 points on the R50 grid), not one patch (6 k points).
 //
 // A warp's cells are cut into chunks of 32 points and run through a three-stage software pipeline,
 // lane <-> point: (1) coalesced loads of ranks_feat / ranks_depth of chunk t + 2, (2) the depth
