@@ -21,7 +21,7 @@ LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "librcbevdet_b200.so")
 OBJ_DIR = os.path.join(PKG, "build")
 
-SOURCES = ["api.cu", "prepare.cu", "prepare_lsd.cu", "pool_plan.cu", "pool_fwd.cu", "pool_fwd_cells.cu", "pool_bwd.cu", "layout.cu", "radar.cu", "bev_shift.cu", "depth_context.cu", "trt_plugin.cu"]
+SOURCES = ["api.cu", "prepare.cu", "prepare_lsd.cu", "pool_plan.cu", "pool_fwd.cu", "pool_fwd_cells.cu", "pool_bwd.cu", "strips.cu", "layout.cu", "radar.cu", "bev_shift.cu", "depth_context.cu", "trt_plugin.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "--expt-extended-lambda", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v",

@@ -1,0 +1,89 @@
+"""Strip plans: the second-level plan of the pooling kernels (csrc/strips.cu).
+
+A strip is a vertical run of 16 pixels of one image column; its frustum points walk along one line
+of BEV cells, so grouping them by (cell, strip) leaves 9-13x fewer partial rows to move than the
+(cell, pixel) pairs of the cell-stationary kernels.  The plan depends only on the ranks (i.e. on the
+calibration), like the ranks themselves: it is built once next to them (`voxel_pooling_prepare_v2`,
+`init_acceleration_v2` in the reference's terms, view_transformer.py:159-178) and reused by every
+forward / backward that runs on those ranks.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+FWD_CHANNELS = (64, 80, 128)
+BWD_CHANNELS = (64, 80)
+
+
+class StripPlan:
+    """desc: rcb_strip_desc; buf: the device plan buffer; status(): 0 when the strip kernels may run."""
+
+    __slots__ = ("desc", "buf", "cell_start", "_status", "_rows")
+
+    def __init__(self, desc, buf, cell_start):
+        self.desc, self.buf, self.cell_start = desc, buf, cell_start
+        self._status = None
+        self._rows = {}
+
+    def status_tensor(self):
+        return self.buf[:4].view(torch.int32)
+
+    def status(self):
+        """Host copy of the status word (one 4-byte read-back, cached)."""
+        if self._status is None:
+            self._status = int(self.status_tensor().item())
+        return self._status
+
+    def rows(self, C):
+        """Scratch for the segment rows (allocated once per channel count, reused by every call on
+        the same stream)."""
+        ws = self._rows.get(C)
+        if ws is None:
+            n = _lib.lib().rcb_strip_rows_bytes(ctypes.byref(self.desc), C)
+            ws = torch.empty(n, dtype=torch.uint8, device=self.buf.device)
+            self._rows[C] = ws
+        return ws
+
+
+def supported(n_img, D, H, W, n_cells):
+    d = _lib.StripDesc()
+    d.n_img, d.D, d.H, d.W, d.n_cells = n_img, D, H, W, n_cells
+    return _lib.lib().rcb_strip_plan_bytes(ctypes.byref(d)) > 0
+
+
+def build(point_cell, cell_start, n_img, D, H, W, n_cells):
+    """Launch the plan kernels on the current stream (no read-back).  Returns None when the geometry is
+    outside the strip kernels' envelope (D > 256, more than 2^24 cells)."""
+    d = _lib.StripDesc()
+    d.n_img, d.D, d.H, d.W, d.n_cells = int(n_img), int(D), int(H), int(W), int(n_cells)
+    lib = _lib.lib()
+    n = lib.rcb_strip_plan_bytes(ctypes.byref(d))
+    if n == 0:
+        return None
+    dev = point_cell.device
+    buf = torch.empty(n, dtype=torch.uint8, device=dev)
+    _lib.check(lib.rcb_strip_plan_build(ctypes.byref(d), _lib.ptr(point_cell), _lib.ptr(cell_start), _lib.ptr(buf),
+                                        n, dev.index, _lib.stream_ptr(dev)), "rcb_strip_plan_build")
+    return StripPlan(d, buf, cell_start)
+
+
+def forward(plan, pool_desc, depth, rows_feat, out):
+    ws = plan.rows(pool_desc.C)
+    dev = out.device
+    _lib.check(_lib.lib().rcb_bev_pool_v2_fwd_strips(
+        ctypes.byref(pool_desc), ctypes.byref(plan.desc), _lib.ptr(plan.buf), _lib.ptr(plan.cell_start),
+        _lib.ptr(depth), _lib.ptr(rows_feat), _lib.ptr(out), _lib.ptr(ws), ws.numel(), dev.index,
+        _lib.stream_ptr(dev)), "rcb_bev_pool_v2_fwd_strips")
+
+
+def backward(plan, pool_desc, out_grad, depth, rows_feat, depth_grad, feat_grad):
+    ws = plan.rows(pool_desc.C)
+    dev = out_grad.device
+    _lib.check(_lib.lib().rcb_bev_pool_v2_bwd_strips(
+        ctypes.byref(pool_desc), ctypes.byref(plan.desc), _lib.ptr(plan.buf), _lib.ptr(plan.cell_start),
+        _lib.ptr(out_grad), _lib.ptr(depth), _lib.ptr(rows_feat), _lib.ptr(depth_grad), _lib.ptr(feat_grad),
+        _lib.ptr(ws), ws.numel(), dev.index, _lib.stream_ptr(dev)), "rcb_bev_pool_v2_bwd_strips")
