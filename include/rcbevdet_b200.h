@@ -199,7 +199,7 @@ int rcb_bev_pool_v2_bwd(const rcb_pool_desc *d, const float *out_grad, const flo
  *         runs -- or has enqueued behind, gated on the same word -- the general entry points.
  *   rows: scratch of rcb_strip_rows_bytes() (one row of C floats per reserved segment; only the used
  *         rows are touched).
- *   cell_start: the dense CSR of rcb_voxel_pooling_prepare_v2 / rcb_pool_build_cellmap.
+ *   cell_start (plan build only): the dense CSR of rcb_voxel_pooling_prepare_v2 / rcb_pool_build_cellmap.
  * Supported: C in {64, 80, 128} forward, {64, 80} backward; D <= 256; B*Z*Y*X <= 2^24.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -213,12 +213,11 @@ size_t rcb_strip_rows_bytes(const rcb_strip_desc *d, int C);
 int rcb_strip_plan_build(const rcb_strip_desc *d, const int *point_cell, const int *cell_start, void *plan,
                          size_t plan_bytes, int device, rcb_stream_t stream);
 int rcb_bev_pool_v2_fwd_strips(const rcb_pool_desc *d, const rcb_strip_desc *sd, const void *plan,
-                               const int *cell_start, const float *depth, const void *feat, float *out,
-                               void *rows, size_t rows_bytes, int device, rcb_stream_t stream);
+                               const float *depth, const void *feat, float *out, void *rows, size_t rows_bytes,
+                               int device, rcb_stream_t stream);
 int rcb_bev_pool_v2_bwd_strips(const rcb_pool_desc *d, const rcb_strip_desc *sd, const void *plan,
-                               const int *cell_start, const float *out_grad, const float *depth,
-                               const void *feat, float *depth_grad, float *feat_grad, void *rows,
-                               size_t rows_bytes, int device, rcb_stream_t stream);
+                               const float *out_grad, const float *depth, const void *feat, float *depth_grad,
+                               float *feat_grad, void *rows, size_t rows_bytes, int device, rcb_stream_t stream);
 
 /* (n_img, C, HW) with image stride `src_img_stride` elements -> (n_img, HW, C) contiguous.
  * Replaces the `feat.contiguous()` transpose copy of bev_pool.py:21 and `out_grad.contiguous()`

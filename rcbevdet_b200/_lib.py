@@ -64,8 +64,8 @@ SIGNATURES = {
     "rcb_strip_plan_bytes": (_sz, [ctypes.POINTER(StripDesc)]),
     "rcb_strip_rows_bytes": (_sz, [ctypes.POINTER(StripDesc), _i]),
     "rcb_strip_plan_build": (_i, [ctypes.POINTER(StripDesc), _vp, _vp, _vp, _sz, _i, _vp]),
-    "rcb_bev_pool_v2_fwd_strips": (_i, [ctypes.POINTER(PoolDesc), ctypes.POINTER(StripDesc)] + [_vp] * 6 + [_sz, _i, _vp]),
-    "rcb_bev_pool_v2_bwd_strips": (_i, [ctypes.POINTER(PoolDesc), ctypes.POINTER(StripDesc)] + [_vp] * 8 + [_sz, _i, _vp]),
+    "rcb_bev_pool_v2_fwd_strips": (_i, [ctypes.POINTER(PoolDesc), ctypes.POINTER(StripDesc)] + [_vp] * 5 + [_sz, _i, _vp]),
+    "rcb_bev_pool_v2_bwd_strips": (_i, [ctypes.POINTER(PoolDesc), ctypes.POINTER(StripDesc)] + [_vp] * 7 + [_sz, _i, _vp]),
     "rcb_planes_to_rows": (_i, [_vp, _vp, _i, _i, _i, _ll, _i, _i, _vp]),
     "rcb_radar_workspace_bytes": (_sz, [ctypes.POINTER(RadarDesc)]),
     "rcb_radar_rcs_scatter": (_i, [ctypes.POINTER(RadarDesc)] + [_vp] * 6 + [_vp, _sz, _i, _vp]),

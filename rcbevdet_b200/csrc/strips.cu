@@ -7,35 +7,35 @@
 // bins of the column walk along a line of cells.  A STRIP is a vertical run of <= 16 pixels of one
 // image column.  On the R50 grid the 1888 frustum points of a strip touch ~70-110 distinct cells:
 // the (cell, strip) SEGMENTS are 9-13x fewer than the (cell, pixel) pairs the cell-stationary kernel
-// gathers a 320-byte context row for (19-28 k against 253 k per sample).
+// gathers a 320-byte context row for (19-28 k against 253 k per sample).  With
 //
-//   out[cell] = sum over the cell's segments of  ( sum over the segment's entries (d, mask) of
-//                                                  sum_v mask_v * depth[d, v] * feat[v, :] )
+//   W[s][v]  = sum of depth[d][v] over the depth bins d whose point (d, v) lies in segment s's cell
+//   out[cell] = sum over the cell's segments s of  W[s][0..15] . feat[strip pixels 0..15][:]
 //
-// so the inner two sums are a small DENSE product with the strip's 16 context rows held in
-// registers (each row is read from memory exactly once per launch), and only one partial row per
-// segment crosses memory:
+// the pooling of a strip is a small DENSE product W (S x 16) . F (16 x C): the strip's 16 context
+// rows sit in registers (each row is read from memory once per launch), W is built in shared memory
+// by one sequential pass per pixel (deterministic), and only one partial row per segment crosses
+// memory.  The backward is the same product transposed: per segment one out_grad row, 16 dot products
+// (every depth bin of a pixel in the segment gets the pixel's dot product as depth_grad) and one
+// rank-1 update W[s] x row of the strip's feat_grad registers.
 //
-//   plan (once per set of ranks; k_strip_plan + k_cellseg_sort)
-//       per strip : ENTRIES (depth bin, 16-bit pixel mask, last-of-segment flag), sorted by
-//                   (cell, depth bin); segment j of strip s owns row s * seg_cap + j of a workspace
-//       per cell  : the sorted list of its segments' row indices (lives in the cell's own slice of
-//                   the point-sorted index space, cell_start[c] + k: no second CSR)
-//   forward  k_fwd_strips  : strip-stationary; registers hold feat[8 px][C/16 ch] per lane, the
-//                            strip's depth slab sits in shared memory; one partial row per segment
-//            k_fwd_combine : cell-stationary; sums a cell's segment rows in list order (fixed ->
-//                            bit-reproducible) and writes the final layout, zeros included
+//   plan (once per set of ranks; k_strip_plan + k_cellseg_index)
+//       per point : LABEL = index of its segment inside its strip (0xffff: dropped)
+//       per segment: the ROW it owns in a workspace
+//       per cell  : seg_start[c] .. seg_start[c+1]: the cell's segments own consecutive rows, in
+//                   (strip, segment) order -- the workspace is cell-major, so the cell-stationary
+//                   passes stream it without any indirection
+//   forward  k_fwd_strips  : W build + dense product, one partial row per segment
+//            k_fwd_combine : cell-stationary; sums a cell's rows in order (fixed -> bit-reproducible)
+//                            and writes the final layout, zeros included
 //   backward k_bwd_spread  : the mirror of combine: out_grad row of a cell -> its segments' rows
-//            k_bwd_strips  : strip-stationary, lane <-> pixel: per segment ONE dot product per pixel
-//                            (depth_grad of every bin of the segment is that value) and one
-//                            rank-1 update of the pixel's feat_grad with the segment's summed weight
+//            k_bwd_strips  : W build, then per segment dot products + feat_grad update
 //
-// Nothing here uses float atomics; integer atomics only hand out list slots, and the lists are
-// sorted afterwards, so every output is bit-reproducible.  Inputs the plan cannot hold (more
-// entries / segments per strip than reserved, which needs cells scattered at random along a
-// column) raise the plan's status word: every kernel here then exits at once and the
-// cell-/pixel-stationary kernels (pool_fwd_cells.cu, pool_bwd.cu), enqueued behind with the same
-// word as their gate, do the work instead.
+// Nothing here uses float atomics; integer atomics only hand out list slots and count, and the
+// lists are sorted before rows are assigned, so every output is bit-reproducible.  Inputs the plan
+// cannot hold (more segments per strip / per group of four strips than reserved, which needs cells
+// scattered at random along a column) raise the plan's status word: every kernel here then exits at
+// once and the caller runs the cell-/pixel-stationary kernels (pool_fwd_cells.cu, pool_bwd.cu).
 #include "common.cuh"
 
 namespace rcb {
@@ -43,13 +43,17 @@ namespace rcb {
 constexpr int kStripV = 16;    // pixels per strip
 constexpr int kStripCols = 4;  // adjacent image columns per CTA (16-byte runs of depth / point_cell)
 constexpr int kCombineCells = 64;
+constexpr int kIndexBlock = 256;  // cells per CTA of k_cellseg_index
+constexpr int kNoLabel = 0xffff;
 
 struct StripGeom {
   int n_img, D, H, W, HW;
   int VC;  // strips per image column
   int UG;  // column groups per image row
-  int seg_cap, ent_cap;
-  int n_strips;
+  int seg_cap;    // segments a strip may have (stride of seg_dst)
+  int group_cap;  // segments the four strips of a CTA may have together (rows of W in shared memory)
+  int ent_cap;    // (cell, depth bin) entries a strip may have while the plan is built
+  int n_strips, n_groups;
   int n_cells;
   int n_list;  // capacity of the per-cell lists (= points)
 };
@@ -68,21 +72,25 @@ static bool make_geom(const rcb_strip_desc *d, StripGeom *g) {
   g->VC = ceil_div(d->H, kStripV), g->UG = ceil_div(d->W, kStripCols);
   g->ent_cap = next_pow2(4 * d->D);
   g->seg_cap = (int)align_up((size_t)3 * d->D, 8);
+  g->group_cap = 768;  // rows of W a CTA can hold: 52 KB of shared memory, four CTAs per SM
   const long long strips = (long long)d->n_img * g->VC * d->W;
+  const long long groups = (long long)d->n_img * g->VC * g->UG;
   const long long points = (long long)d->n_img * d->D * g->HW;
-  if (strips * g->seg_cap >= (1ll << 31) || points >= (1ll << 31) || strips * g->ent_cap >= (1ll << 31))
-    return false;
-  g->n_strips = (int)strips, g->n_cells = d->n_cells, g->n_list = (int)points;
+  if (strips * g->seg_cap >= (1ll << 31) || points >= (1ll << 31) || groups * d->D * 64 >= (1ll << 31)) return false;
+  g->n_strips = (int)strips, g->n_groups = (int)groups, g->n_cells = d->n_cells, g->n_list = (int)points;
   return true;
 }
 
-// plan buffer: header | info | entries | cell_nseg | cellseg_raw | cellseg
+// plan buffer: status | cell_nseg | block_sum (these three zeroed by one memset) | nseg | label |
+//              seg_dst | seg_start | raw
 struct PlanView {
   int *status;
-  int4 *info;
-  unsigned *ent;
-  int *cell_nseg, *raw, *list;
-  size_t bytes;
+  int *cell_nseg, *block_sum;
+  int *nseg;                // [n_strips]
+  unsigned short *label;    // [n_groups][D][16][4]
+  int *seg_dst;             // [n_strips][seg_cap]
+  int *seg_start, *raw;
+  size_t zero_bytes, bytes;
 };
 
 static PlanView plan_view(const StripGeom &g, void *base) {
@@ -90,11 +98,14 @@ static PlanView plan_view(const StripGeom &g, void *base) {
   char *p = static_cast<char *>(base);
   size_t off = 0;
   v.status = reinterpret_cast<int *>(p + off), off += 256;
-  v.info = reinterpret_cast<int4 *>(p + off), off += align_up((size_t)g.n_strips * 16, 256);
-  v.ent = reinterpret_cast<unsigned *>(p + off), off += align_up((size_t)g.n_strips * g.ent_cap * 4, 256);
   v.cell_nseg = reinterpret_cast<int *>(p + off), off += align_up((size_t)g.n_cells * 4, 256);
+  v.block_sum = reinterpret_cast<int *>(p + off), off += align_up((size_t)ceil_div(g.n_cells, kIndexBlock) * 4, 256);
+  v.zero_bytes = off;
+  v.nseg = reinterpret_cast<int *>(p + off), off += align_up((size_t)g.n_strips * 4, 256);
+  v.label = reinterpret_cast<unsigned short *>(p + off), off += align_up((size_t)g.n_groups * g.D * 64 * 2, 256);
+  v.seg_dst = reinterpret_cast<int *>(p + off), off += align_up((size_t)g.n_strips * g.seg_cap * 4, 256);
+  v.seg_start = reinterpret_cast<int *>(p + off), off += align_up((size_t)(g.n_cells + 1) * 4, 256);
   v.raw = reinterpret_cast<int *>(p + off), off += align_up((size_t)g.n_list * 4, 256);
-  v.list = reinterpret_cast<int *>(p + off), off += align_up((size_t)g.n_list * 4, 256);
   v.bytes = off;
   return v;
 }
@@ -110,19 +121,23 @@ __device__ __forceinline__ void strip_block(const StripGeom &g, int bid, int &im
 struct StripPlanParams {
   const int *point_cell, *cell_start;
   int *status;
-  int4 *info;
-  unsigned *ent;
-  int *cell_nseg, *raw;
+  int *nseg;
+  unsigned short *label;
+  int *cell_nseg, *block_sum, *raw;
   StripGeom g;
   int vec4;
 };
 
+// One CTA per group of four adjacent strips, one warp per strip.  The strip's (cell, depth bin)
+// entries (distinct cells among the 16 pixels of a bin, with the pixel mask) are sorted by cell in
+// shared memory; runs of equal cell are the segments; every point gets its segment's index as label.
 __global__ void __launch_bounds__(32 * kStripCols) k_strip_plan(StripPlanParams p) {
   pdl_prologue();
   extern __shared__ __align__(16) unsigned char plan_smem[];
+  __shared__ int s_segs[kStripCols];
   const StripGeom &g = p.g;
   const int D = g.D;
-  int *s_cells = reinterpret_cast<int *>(plan_smem);  // [col][D][16]
+  int *s_cells = reinterpret_cast<int *>(plan_smem);  // [col][D][16]: cells on the way in, labels on the way out
   unsigned long long *s_buf = reinterpret_cast<unsigned long long *>(plan_smem + (size_t)kStripCols * D * kStripV * 4);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int img, vc, u0;
@@ -149,121 +164,184 @@ __global__ void __launch_bounds__(32 * kStripCols) k_strip_plan(StripPlanParams 
   __syncthreads();
 
   const int u = u0 + warp;
-  if (u >= g.W) return;
-  const int strip = (img * g.VC + vc) * g.W + u;
-  const int *cells = s_cells + warp * D * kStripV;
-  unsigned long long *buf = s_buf + (size_t)warp * g.ent_cap;
+  int segs = 0;
+  if (u < g.W) {
+    const int strip = (img * g.VC + vc) * g.W + u;
+    int *cells = s_cells + warp * D * kStripV;
+    unsigned long long *buf = s_buf + (size_t)warp * g.ent_cap;
 
-  // entries: per depth bin the distinct cells among the strip's pixels, two bins per round
-  int n = 0;
-  const int half = lane >> 4, i16 = lane & 15;
-  for (int d0 = 0; d0 < D; d0 += 2) {
-    const int dd = d0 + half;
-    const int cell = dd < D ? cells[dd * kStripV + i16] : -1;
-    const unsigned grp = __match_any_sync(kFull, (unsigned)cell ^ ((unsigned)half << 30));
-    const bool emit = cell >= 0 && lane == __ffs(grp) - 1;
-    const unsigned em = __ballot_sync(kFull, emit);
-    if (emit) {
-      const int pos = n + __popc(em & lanemask_lt());
-      if (pos < g.ent_cap)
-        buf[pos] = ((unsigned long long)cell << 24) | ((unsigned long long)dd << 16) |
-                   (unsigned long long)((grp >> (lane & 16)) & 0xffffu);
-    }
-    n += __popc(em);
-  }
-  if (n > g.ent_cap) {
-    if (lane == 0) {
-      atomicOr(p.status, 1);
-      p.info[strip] = make_int4(0, 0, 0, 0);
-    }
-    return;
-  }
-
-  // sort by (cell, depth bin): bitonic network over the warp's shared-memory slice
-  int n2 = 32;
-  while (n2 < n) n2 <<= 1;
-  for (int i = n + lane; i < n2; i += 32) buf[i] = ~0ull;
-  __syncwarp();
-  for (int k = 2; k <= n2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = lane; t < (n2 >> 1); t += 32) {
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
-        const unsigned long long a = buf[i], b = buf[l];
-        const bool up = (i & k) == 0;
-        if ((a > b) == up) buf[i] = b, buf[l] = a;
+    // entries: per depth bin the distinct cells among the strip's pixels, two bins per round
+    int n = 0;
+    const int half = lane >> 4, i16 = lane & 15;
+    for (int d0 = 0; d0 < D; d0 += 2) {
+      const int dd = d0 + half;
+      const int cell = dd < D ? cells[dd * kStripV + i16] : -1;
+      const unsigned grp = __match_any_sync(kFull, (unsigned)cell ^ ((unsigned)half << 30));
+      const bool emit = cell >= 0 && lane == __ffs(grp) - 1;
+      const unsigned em = __ballot_sync(kFull, emit);
+      if (emit) {
+        const int pos = n + __popc(em & lanemask_lt());
+        if (pos < g.ent_cap)
+          buf[pos] = ((unsigned long long)cell << 24) | ((unsigned long long)dd << 16) |
+                     (unsigned long long)((grp >> (lane & 16)) & 0xffffu);
       }
-      __syncwarp();
+      n += __popc(em);
     }
-  }
+    if (n > g.ent_cap) {
+      if (lane == 0) atomicOr(p.status, 1);
+      n = 0;
+    }
 
-  // segments = runs of equal cell
-  int segs = 0, e_half = n, j_half = 0;
-  bool found = false;
-  const int half_target = n >> 1;
-  for (int e0 = 0; e0 < n; e0 += 32) {
-    const int e = e0 + lane;
-    const bool valid = e < n;
-    const unsigned long long cur = valid ? buf[e] : 0ull;
-    const int cell = (int)(cur >> 24);
-    const bool first = valid && (e == 0 || (int)(buf[e - 1] >> 24) != cell);
-    const bool last = valid && (e + 1 >= n || (int)(buf[e + 1] >> 24) != cell);
-    const unsigned fm = __ballot_sync(kFull, first);
-    const int j = segs + __popc(fm & (lanemask_lt() | (1u << lane))) - 1;
-    if (valid)
-      p.ent[(size_t)strip * g.ent_cap + e] =
-          (unsigned)((cur >> 16) & 0xffu) | ((unsigned)(cur & 0xffffu) << 8) | ((unsigned)last << 24);
-    if (first && j < g.seg_cap) {
-      const int k = atomicAdd(&p.cell_nseg[cell], 1);
-      p.raw[p.cell_start[cell] + k] = strip * g.seg_cap + j;
+    // sort by (cell, depth bin): bitonic network over the warp's shared-memory slice
+    int n2 = 32;
+    while (n2 < n) n2 <<= 1;
+    for (int i = n + lane; i < n2; i += 32) buf[i] = ~0ull;
+    __syncwarp();
+    for (int k = 2; k <= n2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = lane; t < (n2 >> 1); t += 32) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+          const unsigned long long a = buf[i], b = buf[l];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) buf[i] = b, buf[l] = a;
+        }
+        __syncwarp();
+      }
     }
-    const unsigned hm = __ballot_sync(kFull, first && e >= half_target);
-    if (hm && !found) {
-      const int src = __ffs(hm) - 1;
-      e_half = e0 + src, j_half = __shfl_sync(kFull, j, src), found = true;
+
+    // segments = runs of equal cell; label the entry's pixels; register the segment with its cell
+    for (int e0 = 0; e0 < n; e0 += 32) {
+      const int e = e0 + lane;
+      const bool valid = e < n;
+      const unsigned long long cur = valid ? buf[e] : 0ull;
+      const int cell = (int)(cur >> 24);
+      const bool first = valid && (e == 0 || (int)(buf[e - 1] >> 24) != cell);
+      const unsigned fm = __ballot_sync(kFull, first);
+      const int j = segs + __popc(fm & (lanemask_lt() | (1u << lane))) - 1;
+      if (valid) {
+        int *row = cells + (int)((cur >> 16) & 0xffu) * kStripV;
+        for (unsigned m = (unsigned)(cur & 0xffffu); m; m &= m - 1) row[__ffs(m) - 1] = j;
+      }
+      if (first && j < g.seg_cap) {
+        const int k = atomicAdd(&p.cell_nseg[cell], 1);
+        p.raw[p.cell_start[cell] + k] = strip * g.seg_cap + j;
+        atomicAdd(&p.block_sum[cell / kIndexBlock], 1);
+      }
+      segs += __popc(fm);
     }
-    segs += __popc(fm);
+    if (lane == 0) {
+      if (segs > g.seg_cap) atomicOr(p.status, 2);
+      p.nseg[strip] = segs;
+    }
+    // every (segment, pixel) must be ONE run of consecutive depth bins (what a straight ray gives; the
+    // strip kernels build their weights run by run): mark the run starts in a bitmap, a second start
+    // of the same (segment, pixel) refuses the plan
+    __syncwarp();
+    unsigned *seen = reinterpret_cast<unsigned *>(buf);
+    const int nwords = min(segs, g.seg_cap);
+    for (int i = lane; i < nwords; i += 32) seen[i] = 0u;
+    __syncwarp();
+    bool bad = false;
+    for (int d0 = 0; d0 < D; d0 += 2) {
+      const int dd = d0 + half;
+      if (dd >= D) continue;
+      const int l = cells[dd * kStripV + i16];
+      if (l < 0 || l >= nwords) continue;
+      if (dd > 0 && cells[(dd - 1) * kStripV + i16] == l) continue;
+      bad |= (atomicOr(&seen[l], 1u << i16) >> i16) & 1u;
+    }
+    if (bad) atomicOr(p.status, 16);
   }
-  if (!found) j_half = segs;
-  if (lane == 0) {
-    if (segs > g.seg_cap) {
-      atomicOr(p.status, 2);
-      p.info[strip] = make_int4(0, 0, 0, 0);
-    } else {
-      p.info[strip] = make_int4(n, segs, e_half, j_half);
-    }
+  if (lane == 0) s_segs[warp] = segs;
+  __syncthreads();
+  if (tid == 0 && s_segs[0] + s_segs[1] + s_segs[2] + s_segs[3] > g.group_cap) atomicOr(p.status, 8);
+
+  // labels leave as [group][d][pixel][column]: 8 bytes per (d, pixel), consecutive
+  unsigned short *lab = p.label + (size_t)blockIdx.x * D * 64;
+  for (int idx = tid; idx < D * kStripV; idx += 32 * kStripCols) {
+    ushort4 q;
+    q.x = (unsigned short)s_cells[(0 * D) * kStripV + idx];
+    q.y = (unsigned short)s_cells[(1 * D) * kStripV + idx];
+    q.z = (unsigned short)s_cells[(2 * D) * kStripV + idx];
+    q.w = (unsigned short)s_cells[(3 * D) * kStripV + idx];
+    reinterpret_cast<ushort4 *>(lab)[idx] = q;
   }
 }
 
 constexpr int kMaxListSort = 1024;
 
-// per cell: claimed order (atomics) -> ascending row index = (strip, segment) order
-__global__ void __launch_bounds__(256) k_cellseg_sort(const int *cell_nseg, const int *cell_start, const int *raw,
-                                                      int *list, int n_cells, int *status) {
+__device__ __forceinline__ void cswap(int &a, int &b) {
+  const int lo = min(a, b), hi = max(a, b);
+  a = lo, b = hi;
+}
+
+// Per cell: seg_start (exclusive prefix of the segment counts: block totals were counted by the plan
+// kernel, so a CTA only sums the totals of the blocks before it) and, for every segment of the cell,
+// the workspace row it owns: seg_start[c] + its rank in ascending (strip, segment) order -- the
+// claimed order of the atomics never reaches an output.  Lists of <= 8 (all but a few hundred cells
+// next to the cameras) are sorted by their own thread in registers, longer ones by the warp.
+__global__ void __launch_bounds__(kIndexBlock) k_cellseg_index(const int *cell_nseg, const int *block_sum,
+                                                               const int *cell_start, const int *raw, int *seg_start,
+                                                               int *seg_dst, int n_cells, int *status) {
   pdl_prologue();
-  const int lane = threadIdx.x & 31;
-  const int c = (blockIdx.x * 256 + threadIdx.x);
+  __shared__ int s_part[kIndexBlock / 32], s_wsum[kIndexBlock / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = blockIdx.x * kIndexBlock + tid;
   int cnt = 0, cs = 0;
   if (c < n_cells) {
     cnt = cell_nseg[c];
     if (cnt) cs = cell_start[c];
   }
-  if (cnt == 1) list[cs] = raw[cs];
-  unsigned multi = __ballot_sync(kFull, cnt >= 2);
+  int part = 0;
+  for (int i = tid; i < (int)blockIdx.x; i += kIndexBlock) part += block_sum[i];
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += t;
+    part += __shfl_xor_sync(kFull, part, o);
+  }
+  if (lane == 31) s_wsum[warp] = incl;
+  if (lane == 0) s_part[warp] = part;
+  __syncthreads();
+  int start = incl - cnt;
+#pragma unroll
+  for (int w = 0; w < kIndexBlock / 32; ++w) start += s_part[w] + (w < warp ? s_wsum[w] : 0);
+  if (c < n_cells) seg_start[c] = start;
+  if (c == n_cells - 1) seg_start[n_cells] = start + cnt;
+
+  if (cnt >= 1 && cnt <= 8) {
+    int v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = k < cnt ? raw[cs + k] : 0x7fffffff;
+    if (cnt >= 2) {  // Batcher's odd-even merge network for 8 keys (19 exchanges)
+      cswap(v[0], v[1]), cswap(v[2], v[3]), cswap(v[4], v[5]), cswap(v[6], v[7]);
+      cswap(v[0], v[2]), cswap(v[1], v[3]), cswap(v[4], v[6]), cswap(v[5], v[7]);
+      cswap(v[1], v[2]), cswap(v[5], v[6]);
+      cswap(v[0], v[4]), cswap(v[1], v[5]), cswap(v[2], v[6]), cswap(v[3], v[7]);
+      cswap(v[2], v[4]), cswap(v[3], v[5]);
+      cswap(v[1], v[2]), cswap(v[3], v[4]), cswap(v[5], v[6]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < cnt) seg_dst[v[k]] = start + k;
+  }
+  unsigned multi = __ballot_sync(kFull, cnt > 8);
   while (multi) {
     const int src = __ffs(multi) - 1;
     multi &= multi - 1;
-    const int n = __shfl_sync(kFull, cnt, src), b = __shfl_sync(kFull, cs, src);
+    const int n = __shfl_sync(kFull, cnt, src), b = __shfl_sync(kFull, cs, src), st = __shfl_sync(kFull, start, src);
     if (n <= 32) {
       const int id = lane < n ? raw[b + lane] : 0x7fffffff;
       int rank = 0;
       for (int m = 0; m < n; ++m) rank += __shfl_sync(kFull, id, m) < id;
-      if (lane < n) list[b + rank] = id;
+      if (lane < n) seg_dst[id] = st + rank;
     } else if (n <= kMaxListSort) {
       for (int e = lane; e < n; e += 32) {
         const int id = raw[b + e];
         int rank = 0;
         for (int m = 0; m < n; ++m) rank += raw[b + m] < id;
-        list[b + rank] = id;
+        seg_dst[id] = st + rank;
       }
     } else if (lane == 0) {
       atomicOr(status, 4);
@@ -272,417 +350,362 @@ __global__ void __launch_bounds__(256) k_cellseg_sort(const int *cell_nseg, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward
+// strip passes
 // ------------------------------------------------------------------------------------------------
-struct FwdStripsParams {
+struct StripsParams {
   const float *depth;
   const void *feat;
   const int *status;
-  const int4 *info;
-  const unsigned *ent;
-  float *rows;
+  const int *nseg;
+  const unsigned short *label;
+  const int *seg_dst;
+  float *rows;  // forward: written; backward: read
+  float *depth_grad, *feat_grad;
   StripGeom g;
   int vec4;
 };
 
-// lane = (h, j): h = lane / 16 owns pixels 8h .. 8h+7 of the strip, j = lane % 16 owns channels
-// j + 16k, k < CPL (C = 16 * CPL).
-template <typename FeatT, int CPL>
-__global__ void __launch_bounds__(64 * kStripCols, 3) k_fwd_strips(FwdStripsParams p) {
-  pdl_prologue();
-  if (*p.status != 0) return;
-  constexpr int C = 16 * CPL;
-  constexpr int CP = CPL / 2;
-  extern __shared__ __align__(16) unsigned char fs_smem[];
+// Shared prologue of the two strip kernels.  After it: s_W[row][16] holds, for the CTA's four strips
+// back to back (strip k's segment s is row base[k] + s), the summed depth weight of every (segment,
+// pixel); s_dst[row] the workspace row of the segment.
+struct StripCta {
+  int img, vc, u0, v0, strip0;
+  int base[kStripCols + 1];
+  // base[i] without dynamic indexing (keeps the array in registers)
+  __device__ __forceinline__ int at(int i) const {
+    int r = base[0];
+#pragma unroll
+    for (int k = 1; k <= kStripCols; ++k) r = i == k ? base[k] : r;
+    return r;
+  }
+};
+
+__device__ __forceinline__ void strip_prologue(const StripsParams &p, float *s_W, int *s_dst, StripCta &c) {
   const StripGeom &g = p.g;
   const int D = g.D;
-  float *s_w = reinterpret_cast<float *>(fs_smem);  // [col][D][16]
-  unsigned *s_ent = reinterpret_cast<unsigned *>(fs_smem + (size_t)kStripCols * D * kStripV * 4);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int img, vc, u0;
-  strip_block(g, blockIdx.x, img, vc, u0);
-  const int v0 = vc * kStripV;
-
-  for (int idx = tid; idx < D * kStripV; idx += 64 * kStripCols) {
-    const int d = idx >> 4, i = idx & 15, v = v0 + i;
-    float c[kStripCols] = {0.f, 0.f, 0.f, 0.f};
-    if (v < g.H) {
-      const float *src = p.depth + ((size_t)(img * D + d) * g.HW + (size_t)v * g.W + u0);
-      if (p.vec4) {
-        const float4 q = ld_stream_f4(reinterpret_cast<const float4 *>(src));
-        c[0] = q.x, c[1] = q.y, c[2] = q.z, c[3] = q.w;
-      } else {
+  strip_block(g, blockIdx.x, c.img, c.vc, c.u0);
+  c.v0 = c.vc * kStripV;
+  c.strip0 = (c.img * g.VC + c.vc) * g.W + c.u0;
+  c.base[0] = 0;
 #pragma unroll
-        for (int k = 0; k < kStripCols; ++k)
-          if (u0 + k < g.W) c[k] = ld_stream_f32(src + k);
+  for (int k = 0; k < kStripCols; ++k) c.base[k + 1] = c.base[k] + (c.u0 + k < g.W ? p.nseg[c.strip0 + k] : 0);
+  const int total = c.base[kStripCols];
+  for (int i = tid; i < total * 4; i += 32 * kStripCols) reinterpret_cast<float4 *>(s_W)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    const int b0 = c.at(warp), n = c.at(warp + 1) - b0;
+    for (int q = lane; q < n; q += 32) s_dst[b0 + q] = p.seg_dst[(size_t)(c.strip0 + warp) * g.seg_cap + q];
+  }
+  __syncthreads();
+  // W[segment][pixel] = sum of the pixel's depth weights over its run of bins with that label.  A
+  // straight ray is inside a (convex) cell over ONE interval of depth, so every (segment, pixel) has
+  // exactly one run (the plan checks it and refuses inputs where it does not hold) and a run's sum is
+  // simply stored.  Two threads per (pixel, column), each taking half of the depth bins in chunks of
+  // 32 that are loaded as a batch (one memory latency per chunk) and then walked in registers.  A run
+  // belongs to the thread in whose half it starts; that thread follows it across the boundary.
+  {
+    const int dh = tid >> 6, vk = tid & 63, v = vk >> 2, k = vk & 3;
+    if (c.v0 + v < g.H && c.u0 + k < g.W) {
+      const int dlen = (D + 1) >> 1, d_begin = dh * dlen, d_end = min(D, d_begin + dlen);
+      const unsigned short *lab = p.label + (size_t)blockIdx.x * D * 64 + vk;
+      const float *w = p.depth + ((size_t)c.img * D * g.HW + (size_t)(c.v0 + v) * g.W + c.u0 + k);
+      float *wrow = s_W + (size_t)c.at(k) * kStripV + v;
+      int cur = d_begin > 0 ? (int)lab[(size_t)(d_begin - 1) * 64] : kNoLabel;
+      bool own = false;
+      float acc = 0.f;
+      for (int d0 = d_begin; d0 < d_end; d0 += 32) {
+        int l[32];
+        float x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const bool ok = d0 + i < d_end;
+          l[i] = ok ? (int)lab[(size_t)(d0 + i) * 64] : -1;
+          x[i] = ok ? ld_stream_f32(w + (size_t)(d0 + i) * g.HW) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (l[i] < 0) break;
+          if (l[i] != cur) {
+            if (own && cur != kNoLabel) wrow[cur * kStripV] = acc;
+            cur = l[i], acc = 0.f, own = true;
+          }
+          acc += x[i];
+        }
+      }
+      if (own && cur != kNoLabel) {
+        for (int dd = d_end; dd < D && (int)lab[(size_t)dd * 64] == cur; ++dd) acc += ld_stream_f32(w + (size_t)dd * g.HW);
+        wrow[cur * kStripV] = acc;
       }
     }
-#pragma unroll
-    for (int k = 0; k < kStripCols; ++k) s_w[(k * D + d) * kStripV + i] = c[k];
   }
+  __syncthreads();
+}
 
-  const int col = warp >> 1, part = warp & 1;
-  const int u = u0 + col;
-  const bool active = u < g.W;
-  const int strip = (img * g.VC + vc) * g.W + (active ? u : 0);
-  const int4 inf = active ? p.info[strip] : make_int4(0, 0, 0, 0);
-  const int e_lo = part ? inf.z : 0, e_hi = part ? inf.x : inf.z;
-  int seg = part ? inf.w : 0;
-  unsigned *ents = s_ent + col * g.ent_cap;
-  for (int e = e_lo + lane; e < e_hi; e += 32) ents[e] = p.ent[(size_t)strip * g.ent_cap + e];
-
-  const int h = lane >> 4, j = lane & 15;
-  float f[8][CPL];
+// lane = (h, j): h = lane / 16 owns pixels 8h .. 8h+7 of the strip, j = lane % 16 owns channels
+// j + 16k, k < CPL (C = 16 * CPL).  fp[tp][k] = (feat[pixel 2tp][channel], feat[pixel 2tp+1][channel]):
+// the packed FMAs pair two PIXELS, so their weight operand is a register pair straight out of the
+// 128-bit load of the W row.
+template <typename FeatT, int CPL>
+__device__ __forceinline__ void load_strip_feat(const StripsParams &p, const StripCta &c, int col, bool wanted,
+                                                float2 (&fp)[4][CPL]) {
+  constexpr int C = 16 * CPL;
+  const StripGeom &g = p.g;
+  const int lane = threadIdx.x & 31, h = lane >> 4, j = lane & 15;
   const FeatT *feat = static_cast<const FeatT *>(p.feat);
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
-    const int v = v0 + 8 * h + t;
-    const bool ok = active && v < g.H && e_lo < e_hi;
-    const FeatT *row = feat + ((size_t)img * g.HW + (size_t)(ok ? v : 0) * g.W + (ok ? u : 0)) * C + j;
+    const int v = c.v0 + 8 * h + t;
+    const bool ok = wanted && v < g.H;
+    const FeatT *row = feat + ((size_t)c.img * g.HW + (size_t)(ok ? v : 0) * g.W + (ok ? c.u0 + col : 0)) * C + j;
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) f[t][k] = ok ? to_f32<FeatT>(row[16 * k]) : 0.f;
+    for (int k = 0; k < CPL; ++k) {
+      const float x = ok ? to_f32<FeatT>(row[16 * k]) : 0.f;
+      if (t & 1) fp[t >> 1][k].y = x;
+      else fp[t >> 1][k].x = x;
+    }
   }
-  __syncthreads();
-  if (e_lo >= e_hi) return;
+}
 
-  const float *wcol = s_w + col * D * kStripV + 8 * h;
-  float2 acc[CP > 0 ? CP : 1];
-  float2 acc_l = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int k = 0; k < CP; ++k) acc[k] = make_float2(0.f, 0.f);
-  float *dst = p.rows + ((size_t)strip * g.seg_cap + seg) * C + j;
-  const int mshift = 8 + 8 * h;
+template <typename FeatT, int CPL>
+__global__ void __launch_bounds__(32 * kStripCols, CPL <= 5 ? 4 : 2) k_fwd_strips(StripsParams p) {
+  pdl_prologue();
+  if (*p.status != 0) return;
+  constexpr int C = 16 * CPL;
+  extern __shared__ __align__(16) unsigned char fs_smem[];
+  float *s_W = reinterpret_cast<float *>(fs_smem);
+  int *s_dst = reinterpret_cast<int *>(fs_smem + (size_t)p.g.group_cap * kStripV * 4);
+  const int lane = threadIdx.x & 31, col = threadIdx.x >> 5;
+  StripCta c;
+  // the feature rows are requested before the W build so that their latency hides behind it
+  strip_block(p.g, blockIdx.x, c.img, c.vc, c.u0);
+  c.v0 = c.vc * kStripV;
+  float2 fp[4][CPL];
+  load_strip_feat<FeatT, CPL>(p, c, col, c.u0 + col < p.g.W, fp);
+  strip_prologue(p, s_W, s_dst, c);
 
-  for (int e = e_lo; e < e_hi; ++e) {
-    const unsigned word = ents[e];
-    const int d = word & 255;
-    const unsigned m8 = (word >> mshift) & 255u;
-    const float4 wa = *reinterpret_cast<const float4 *>(wcol + d * kStripV);
-    const float4 wb = *reinterpret_cast<const float4 *>(wcol + d * kStripV + 4);
-    float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+  const int h = lane >> 4, j = lane & 15;
+  const int b0 = c.at(col), n = c.at(col + 1) - b0;
+  const float *wrow = s_W + (size_t)b0 * kStripV + 8 * h;
+  const int *dsts = s_dst + b0;
+#pragma unroll 2
+  for (int sg = 0; sg < n; ++sg) {
+    const float4 wa = *reinterpret_cast<const float4 *>(wrow + sg * kStripV);
+    const float4 wb = *reinterpret_cast<const float4 *>(wrow + sg * kStripV + 4);
+    const float2 w2[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y), make_float2(wb.z, wb.w)};
+    float a[CPL];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) ww[t] = (m8 >> t) & 1u ? ww[t] : 0.f;
+    for (int k = 0; k < CPL; ++k) {
+      float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int tp = 0; tp < 4; ++tp) acc = __ffma2_rn(fp[tp][k], w2[tp], acc);
+      a[k] = acc.x + acc.y;
+    }
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) a[k] += __shfl_xor_sync(kFull, a[k], 16);
+    float *dst = p.rows + (size_t)dsts[sg] * C + j;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k)
+      if ((k & 1) == h) dst[16 * k] = a[k];
+  }
+}
+
+// Backward: same layout, fgp = the strip's feat_grad as pixel pairs.  Per segment the out_grad row
+// arrives as CPL coalesced words per lane (prefetched one segment ahead); the dot products of all 16
+// pixels cost CPL * 4 packed FMAs + a transposed butterfly over the 16 channel lanes (8 shuffles: lane
+// j ends up with pixel (j >> 1) % 8), and overwrite the segment's W row once it has been consumed by
+// the feat_grad update.  At the end depth_grad[d][v] = W[label[d][v]][v], written coalesced.
+template <typename FeatT, int CPL>
+__global__ void __launch_bounds__(32 * kStripCols, 4) k_bwd_strips(StripsParams p) {
+  pdl_prologue();
+  if (*p.status != 0) return;
+  constexpr int C = 16 * CPL;
+  extern __shared__ __align__(16) unsigned char bs_smem[];
+  float *s_W = reinterpret_cast<float *>(bs_smem);
+  int *s_dst = reinterpret_cast<int *>(bs_smem + (size_t)p.g.group_cap * kStripV * 4);
+  const StripGeom &g = p.g;
+  const int tid = threadIdx.x, lane = tid & 31, col = tid >> 5;
+  StripCta c;
+  strip_block(g, blockIdx.x, c.img, c.vc, c.u0);
+  c.v0 = c.vc * kStripV;
+  const bool active = c.u0 + col < g.W;
+  float2 fp[4][CPL], fgp[4][CPL];
+  load_strip_feat<FeatT, CPL>(p, c, col, active, fp);
+#pragma unroll
+  for (int tp = 0; tp < 4; ++tp)
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) fgp[tp][k] = make_float2(0.f, 0.f);
+  strip_prologue(p, s_W, s_dst, c);
+
+  const int h = lane >> 4, j = lane & 15;
+  const int b0 = c.at(col), n = c.at(col + 1) - b0;
+  if (n > 0) {
+    float *wrow = s_W + (size_t)b0 * kStripV + 8 * h;
+    const int *dsts = s_dst + b0;
+    const int my_t = (j >> 1) & 7;  // the pixel (of this half) whose dot product ends up in this lane
+    const bool b8 = j & 8, b4 = j & 4, b2 = j & 2, writer = (j & 1) == 0;
+    float gr[CPL];
+    {
+      const float *src = p.rows + (size_t)dsts[0] * C + j;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) gr[k] = src[16 * k];
+    }
+    for (int sg = 0; sg < n; ++sg) {
+      float gn[CPL];
+      {
+        const float *src = p.rows + (size_t)dsts[sg + 1 < n ? sg + 1 : sg] * C + j;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) gn[k] = src[16 * k];
+      }
+      const float4 wa = *reinterpret_cast<const float4 *>(wrow + sg * kStripV);
+      const float4 wb = *reinterpret_cast<const float4 *>(wrow + sg * kStripV + 4);
+      const float2 w2[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y), make_float2(wb.z, wb.w)};
+      float2 dp[4];
+#pragma unroll
+      for (int tp = 0; tp < 4; ++tp) dp[tp] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const float2 g2 = make_float2(gr[k], gr[k]);
+#pragma unroll
+        for (int tp = 0; tp < 4; ++tp) {
+          dp[tp] = __ffma2_rn(fp[tp][k], g2, dp[tp]);
+          fgp[tp][k] = __ffma2_rn(w2[tp], g2, fgp[tp][k]);
+        }
+      }
+      // transposed butterfly over the 16 channel lanes of the half
+      const float2 sa = b8 ? dp[0] : dp[2], sb = b8 ? dp[1] : dp[3];
+      float2 ka = b8 ? dp[2] : dp[0], kb = b8 ? dp[3] : dp[1];
+      ka.x += __shfl_xor_sync(kFull, sa.x, 8), ka.y += __shfl_xor_sync(kFull, sa.y, 8);
+      kb.x += __shfl_xor_sync(kFull, sb.x, 8), kb.y += __shfl_xor_sync(kFull, sb.y, 8);
+      const float2 s2 = b4 ? ka : kb;
+      float2 k2 = b4 ? kb : ka;
+      k2.x += __shfl_xor_sync(kFull, s2.x, 4), k2.y += __shfl_xor_sync(kFull, s2.y, 4);
+      const float s3 = b2 ? k2.x : k2.y;
+      float dot = b2 ? k2.y : k2.x;
+      dot += __shfl_xor_sync(kFull, s3, 2);
+      dot += __shfl_xor_sync(kFull, dot, 1);
+      if (writer) wrow[sg * kStripV + my_t] = dot;  // every lane of the half read the row above (shuffles in between)
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) gr[k] = gn[k];
+    }
+  }
+
+  if (active) {
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-      const float2 w2 = make_float2(ww[t], ww[t]);
+      const int v = c.v0 + 8 * h + t;
+      if (v >= g.H) continue;
+      float *row = p.feat_grad + ((size_t)c.img * g.HW + (size_t)v * g.W + c.u0 + col) * C + j;
 #pragma unroll
-      for (int k = 0; k < CP; ++k) acc[k] = __ffma2_rn(make_float2(f[t][2 * k], f[t][2 * k + 1]), w2, acc[k]);
+      for (int k = 0; k < CPL; ++k) st_stream_f32(row + 16 * k, (t & 1) ? fgp[t >> 1][k].y : fgp[t >> 1][k].x);
     }
-    if (CPL & 1) {
+  }
+  __syncthreads();
+  const int D = g.D;
+  const ushort4 *lab = reinterpret_cast<const ushort4 *>(p.label + (size_t)blockIdx.x * D * 64);
+  for (int idx = tid; idx < D * kStripV; idx += 32 * kStripCols) {
+    const int d = idx >> 4, i = idx & 15, vv = c.v0 + i;
+    if (vv >= g.H) continue;
+    const ushort4 q = lab[idx];
+    const int l[kStripCols] = {q.x, q.y, q.z, q.w};
+    float o[kStripCols];
 #pragma unroll
-      for (int t = 0; t < 8; t += 2)
-        acc_l = __ffma2_rn(make_float2(f[t][CPL - 1], f[t + 1][CPL - 1]), make_float2(ww[t], ww[t + 1]), acc_l);
-    }
-    if (word >> 24) {  // last entry of the segment: fold the two pixel halves, write the partial row
-      float a[CPL];
+    for (int k = 0; k < kStripCols; ++k) o[k] = l[k] != kNoLabel ? s_W[(size_t)(c.base[k] + l[k]) * kStripV + i] : 0.f;
+    float *dst = p.depth_grad + ((size_t)(c.img * D + d) * g.HW + (size_t)vv * g.W + c.u0);
+    if (p.vec4) {
+      st_stream_f4(reinterpret_cast<float4 *>(dst), make_float4(o[0], o[1], o[2], o[3]));
+    } else {
 #pragma unroll
-      for (int k = 0; k < CP; ++k) a[2 * k] = acc[k].x, a[2 * k + 1] = acc[k].y, acc[k] = make_float2(0.f, 0.f);
-      if (CPL & 1) a[CPL - 1] = acc_l.x + acc_l.y, acc_l = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int k = 0; k < CPL; ++k) a[k] += __shfl_xor_sync(kFull, a[k], 16);
-#pragma unroll
-      for (int k = 0; k < CPL; ++k)
-        if ((k & 1) == h) dst[16 * k] = a[k];
-      dst += C;
+      for (int k = 0; k < kStripCols; ++k)
+        if (c.u0 + k < g.W) st_stream_f32(dst + k, o[k]);
     }
   }
 }
 
 struct CombineParams {
   const int *status;
-  const int *cell_nseg, *cell_start, *list;
-  float *rows;        // forward: read; backward spread: written
-  float *out;         // forward: the pooled tensor; backward spread: out_grad (read)
+  const int *seg_start;
+  float *rows;  // forward: read; backward spread: written
+  float *out;   // forward: the pooled tensor; backward spread: out_grad (read)
   int cps, tiles_per_sample, layout;
 };
 
-// lane = (h, j): half-warp h pools one cell, lane j owns channels j + 16k
+// Four lanes per cell (eight cells per warp): lane `sub` owns the 128-bit channel quads sub + 4q of the
+// cell's rows.  The rows of consecutive cells are consecutive in the workspace: the CTA streams one
+// contiguous piece of it.  A (B, C, cells) store instruction writes four channel rows x eight
+// consecutive cells (whole 32-byte sectors).  No shared memory, no barrier, no indirection.
 template <int CPL>
 __global__ void __launch_bounds__(256) k_fwd_combine(CombineParams p) {
   pdl_prologue();
   if (*p.status != 0) return;
   constexpr int C = 16 * CPL;
-  constexpr int kPitch = kCombineCells + 1;
-  extern __shared__ __align__(16) float cb_tile[];  // [C][kPitch]   (B, C, cells) layout only
-  __shared__ int s_cnt[kCombineCells], s_cs[kCombineCells];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x / p.tiles_per_sample, c0 = (blockIdx.x % p.tiles_per_sample) * kCombineCells;
-  if (tid < kCombineCells) {
-    int cnt = 0, cs = 0;
-    if (c0 + tid < p.cps) {
-      const size_t gc = (size_t)b * p.cps + c0 + tid;
-      cnt = p.cell_nseg[gc];
-      cs = p.cell_start[gc];
-    }
-    s_cnt[tid] = cnt, s_cs[tid] = cs;
+  const int cell = c0 + warp * 8 + (lane >> 2), sub = lane & 3;
+  if (cell >= p.cps) return;
+  const size_t gc = (size_t)b * p.cps + cell;
+  const int r0 = p.seg_start[gc], r1 = p.seg_start[gc + 1];
+  float4 acc[CPL];
+#pragma unroll
+  for (int q = 0; q < CPL; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 *src = reinterpret_cast<const float4 *>(p.rows + (size_t)r0 * C) + sub;
+  for (int r = r0; r < r1; ++r, src += C / 4) {
+    float4 v[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) v[q] = src[4 * q];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) acc[q].x += v[q].x, acc[q].y += v[q].y, acc[q].z += v[q].z, acc[q].w += v[q].w;
   }
-  __syncthreads();
-  const int h = lane >> 4, j = lane & 15;
-  const bool to_tile = p.layout == RCB_LAYOUT_B_C_CELLS;
-#pragma unroll 1
-  for (int r = 0; r < kCombineCells / 16; ++r) {
-    const int slot = warp * (kCombineCells / 8) + 2 * r + h;
-    const int cnt = s_cnt[slot], cs = s_cs[slot];
-    float a[CPL];
+  if (p.layout == RCB_LAYOUT_B_C_CELLS) {
+    float *dst = p.out + (size_t)b * C * p.cps + cell;
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) a[k] = 0.f;
-    for (int k0 = 0; k0 < cnt; k0 += 4) {
-      int id[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) id[q] = k0 + q < cnt ? p.list[cs + k0 + q] : -1;
-      float v[4][CPL];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float *src = p.rows + (size_t)(id[q] < 0 ? 0 : id[q]) * C + j;
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) v[q][k] = id[q] >= 0 ? src[16 * k] : 0.f;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) a[k] += v[q][k];
+    for (int q = 0; q < CPL; ++q) {
+      const size_t ch = (size_t)(sub + 4 * q) * 4;
+      st_stream_f32(dst + (ch + 0) * p.cps, acc[q].x);
+      st_stream_f32(dst + (ch + 1) * p.cps, acc[q].y);
+      st_stream_f32(dst + (ch + 2) * p.cps, acc[q].z);
+      st_stream_f32(dst + (ch + 3) * p.cps, acc[q].w);
     }
-    if (to_tile) {
+  } else {
+    float4 *dst = reinterpret_cast<float4 *>(p.out + gc * C) + sub;
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) cb_tile[(j + 16 * k) * kPitch + slot] = a[k];
-    } else if (c0 + slot < p.cps) {
-      float *dst = p.out + ((size_t)b * p.cps + c0 + slot) * C + j;
-#pragma unroll
-      for (int k = 0; k < CPL; ++k) st_stream_f32(dst + 16 * k, a[k]);
-    }
-  }
-  if (!to_tile) return;
-  __syncthreads();
-  for (int ch = warp; ch < C; ch += 8) {
-    float *dst = p.out + ((size_t)b * C + ch) * p.cps + c0;
-    if (c0 + lane < p.cps) st_stream_f32(dst + lane, cb_tile[ch * kPitch + lane]);
-    if (c0 + 32 + lane < p.cps) st_stream_f32(dst + 32 + lane, cb_tile[ch * kPitch + 32 + lane]);
+    for (int q = 0; q < CPL; ++q) st_stream_f4(dst + 4 * q, acc[q]);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
+// the mirror image of k_fwd_combine: the out_grad row of a cell goes to each of the cell's segments
 template <int CPL>
 __global__ void __launch_bounds__(256) k_bwd_spread(CombineParams p) {
   pdl_prologue();
   if (*p.status != 0) return;
   constexpr int C = 16 * CPL;
-  constexpr int kPitch = kCombineCells + 1;
-  extern __shared__ __align__(16) float cb_tile[];
-  __shared__ int s_cnt[kCombineCells], s_cs[kCombineCells];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x / p.tiles_per_sample, c0 = (blockIdx.x % p.tiles_per_sample) * kCombineCells;
-  const bool from_tile = p.layout == RCB_LAYOUT_B_C_CELLS;
-  if (tid < kCombineCells) {
-    int cnt = 0, cs = 0;
-    if (c0 + tid < p.cps) {
-      const size_t gc = (size_t)b * p.cps + c0 + tid;
-      cnt = p.cell_nseg[gc];
-      cs = p.cell_start[gc];
+  const int cell = c0 + warp * 8 + (lane >> 2), sub = lane & 3;
+  if (cell >= p.cps) return;
+  const size_t gc = (size_t)b * p.cps + cell;
+  const int r0 = p.seg_start[gc], r1 = p.seg_start[gc + 1];
+  if (r0 >= r1) return;
+  float4 a[CPL];
+  if (p.layout == RCB_LAYOUT_B_C_CELLS) {
+    const float *src = p.out + (size_t)b * C * p.cps + cell;
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const size_t ch = (size_t)(sub + 4 * q) * 4;
+      a[q] = make_float4(ld_stream_f32(src + (ch + 0) * p.cps), ld_stream_f32(src + (ch + 1) * p.cps),
+                         ld_stream_f32(src + (ch + 2) * p.cps), ld_stream_f32(src + (ch + 3) * p.cps));
     }
-    s_cnt[tid] = cnt, s_cs[tid] = cs;
+  } else {
+    const float4 *src = reinterpret_cast<const float4 *>(p.out + gc * C) + sub;
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) a[q] = ld_stream_f4(src + 4 * q);
   }
-  if (from_tile) {
-    for (int ch = warp; ch < C; ch += 8) {
-      const float *src = p.out + ((size_t)b * C + ch) * p.cps + c0;
-      cb_tile[ch * kPitch + lane] = c0 + lane < p.cps ? ld_stream_f32(src + lane) : 0.f;
-      cb_tile[ch * kPitch + 32 + lane] = c0 + 32 + lane < p.cps ? ld_stream_f32(src + 32 + lane) : 0.f;
-    }
-  }
-  __syncthreads();
-  const int h = lane >> 4, j = lane & 15;
-#pragma unroll 1
-  for (int r = 0; r < kCombineCells / 16; ++r) {
-    const int slot = warp * (kCombineCells / 8) + 2 * r + h;
-    const int cnt = s_cnt[slot], cs = s_cs[slot];
-    if (cnt == 0) continue;
-    float a[CPL];
-    if (from_tile) {
+  float4 *dst = reinterpret_cast<float4 *>(p.rows + (size_t)r0 * C) + sub;
+  for (int r = r0; r < r1; ++r, dst += C / 4) {
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) a[k] = cb_tile[(j + 16 * k) * kPitch + slot];
-    } else {
-      const float *src = p.out + ((size_t)b * p.cps + c0 + slot) * C + j;
-#pragma unroll
-      for (int k = 0; k < CPL; ++k) a[k] = ld_stream_f32(src + 16 * k);
-    }
-    for (int k0 = 0; k0 < cnt; ++k0) {
-      float *dst = p.rows + (size_t)p.list[cs + k0] * C + j;
-#pragma unroll
-      for (int k = 0; k < CPL; ++k) dst[16 * k] = a[k];
-    }
-  }
-}
-
-struct BwdStripsParams {
-  const float *depth;
-  const void *feat;
-  const int *status;
-  const int4 *info;
-  const unsigned *ent;
-  const float *rows;
-  float *depth_grad, *feat_grad;
-  StripGeom g;
-  int vec4;
-};
-
-// lane = (hc, v): v = lane % 16 is the strip's pixel, hc = lane / 16 owns channels [hc*C/2, (hc+1)*C/2)
-// as Q = C/8 float4's.
-template <typename FeatT, int Q>
-__global__ void __launch_bounds__(64 * kStripCols, 2) k_bwd_strips(BwdStripsParams p) {
-  pdl_prologue();
-  if (*p.status != 0) return;
-  constexpr int C = 8 * Q;
-  constexpr int NL = (C + 31) / 32;  // row elements per lane when a warp moves one row
-  constexpr int kFgPitch = C + 4;
-  extern __shared__ __align__(16) unsigned char bs_smem[];
-  const StripGeom &g = p.g;
-  const int D = g.D;
-  float *s_w = reinterpret_cast<float *>(bs_smem);  // [col][D][16]: depth on the way in, depth_grad on the way out
-  size_t off = (size_t)kStripCols * D * kStripV * 4;
-  unsigned *s_ent = reinterpret_cast<unsigned *>(bs_smem + off);
-  off += (size_t)kStripCols * g.ent_cap * 4;
-  float *s_g = reinterpret_cast<float *>(bs_smem + off);  // [warp][C]
-  off += (size_t)2 * kStripCols * C * 4;
-  float *s_fg = reinterpret_cast<float *>(bs_smem + off);  // [col][16][kFgPitch]
-  off += (size_t)kStripCols * kStripV * kFgPitch * 4;
-  unsigned *s_kept = reinterpret_cast<unsigned *>(bs_smem + off);  // [col][D]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int img, vc, u0;
-  strip_block(g, blockIdx.x, img, vc, u0);
-  const int v0 = vc * kStripV;
-
-  for (int idx = tid; idx < D * kStripV; idx += 64 * kStripCols) {
-    const int d = idx >> 4, i = idx & 15, v = v0 + i;
-    float c[kStripCols] = {0.f, 0.f, 0.f, 0.f};
-    if (v < g.H) {
-      const float *src = p.depth + ((size_t)(img * D + d) * g.HW + (size_t)v * g.W + u0);
-      if (p.vec4) {
-        const float4 q = ld_stream_f4(reinterpret_cast<const float4 *>(src));
-        c[0] = q.x, c[1] = q.y, c[2] = q.z, c[3] = q.w;
-      } else {
-#pragma unroll
-        for (int k = 0; k < kStripCols; ++k)
-          if (u0 + k < g.W) c[k] = ld_stream_f32(src + k);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < kStripCols; ++k) s_w[(k * D + d) * kStripV + i] = c[k];
-  }
-  for (int idx = tid; idx < kStripCols * D; idx += 64 * kStripCols) s_kept[idx] = 0u;
-
-  const int col = warp >> 1, part = warp & 1;
-  const int u = u0 + col;
-  const bool active = u < g.W;
-  const int strip = (img * g.VC + vc) * g.W + (active ? u : 0);
-  const int4 inf = active ? p.info[strip] : make_int4(0, 0, 0, 0);
-  const int e_lo = part ? inf.z : 0, e_hi = part ? inf.x : inf.z;
-  const int seg_lo = part ? inf.w : 0, seg_hi = part ? inf.y : inf.w;
-  const int nseg = seg_hi - seg_lo;
-  unsigned *ents = s_ent + col * g.ent_cap;
-  for (int e = e_lo + lane; e < e_hi; e += 32) ents[e] = p.ent[(size_t)strip * g.ent_cap + e];
-
-  const int hc = lane >> 4, v = lane & 15;
-  const bool pix_ok = active && v0 + v < g.H;
-  const size_t pixel = (size_t)img * g.HW + (size_t)(pix_ok ? v0 + v : 0) * g.W + (pix_ok ? u : 0);
-  float4 f[Q], fg[Q];
-  {
-    const char *row = static_cast<const char *>(p.feat) + (pixel * C + (size_t)hc * (C / 2)) * sizeof(FeatT);
-#pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      f[q] = pix_ok && nseg > 0 ? Row4<FeatT>::load_bytes(row + (size_t)q * 4 * sizeof(FeatT)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      fg[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
-  // segment rows two ahead in registers
-  const float *rowp = p.rows + ((size_t)strip * g.seg_cap + seg_lo) * C;
-  float r0[NL], r1[NL], r2[NL];
-  auto load_row = [&](int jj, float(&r)[NL]) {
-#pragma unroll
-    for (int k = 0; k < NL; ++k) r[k] = (jj < nseg && 32 * k + lane < C) ? rowp[(size_t)jj * C + 32 * k + lane] : 0.f;
-  };
-  load_row(0, r0), load_row(1, r1), load_row(2, r2);
-  __syncthreads();
-
-  float *wcol = s_w + col * D * kStripV;
-  float *gs = s_g + warp * C;
-  int e = e_lo;
-  for (int jj = 0; jj < nseg; ++jj) {
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < NL; ++k)
-      if (32 * k + lane < C) gs[32 * k + lane] = r0[k];
-#pragma unroll
-    for (int k = 0; k < NL; ++k) r0[k] = r1[k], r1[k] = r2[k];
-    load_row(jj + 3, r2);
-    __syncwarp();
-    // the segment's summed weight of this lane's pixel
-    float wsum = 0.f;
-    int e1 = e;
-    for (;; ++e1) {
-      const unsigned word = ents[e1];
-      if ((word >> (8 + v)) & 1u) wsum += wcol[(word & 255u) * kStripV + v];
-      if (word >> 24) break;
-    }
-    // dot(out_grad row, feat row of the pixel) and feat_grad += wsum * out_grad row
-    float2 d0 = make_float2(0.f, 0.f), d1 = make_float2(0.f, 0.f);
-    const float2 w2 = make_float2(wsum, wsum);
-    const float4 *g4 = reinterpret_cast<const float4 *>(gs + hc * (C / 2));
-#pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      const float4 gq = g4[q];
-      const float2 glo = make_float2(gq.x, gq.y), ghi = make_float2(gq.z, gq.w);
-      d0 = __ffma2_rn(glo, make_float2(f[q].x, f[q].y), d0);
-      d1 = __ffma2_rn(ghi, make_float2(f[q].z, f[q].w), d1);
-      const float2 a = __ffma2_rn(glo, w2, make_float2(fg[q].x, fg[q].y));
-      const float2 bq = __ffma2_rn(ghi, w2, make_float2(fg[q].z, fg[q].w));
-      fg[q] = make_float4(a.x, a.y, bq.x, bq.y);
-    }
-    float dot = (d0.x + d0.y) + (d1.x + d1.y);
-    dot += __shfl_xor_sync(kFull, dot, 16);
-    // depth_grad of every bin of the segment that holds this pixel
-    for (;; ++e) {
-      const unsigned word = ents[e];
-      const int d = word & 255u;
-      if (hc == 0 && ((word >> (8 + v)) & 1u)) wcol[d * kStripV + v] = dot;
-      if (lane == 0) atomicOr(&s_kept[col * D + d], (word >> 8) & 0xffffu);
-      if (word >> 24) {
-        ++e;
-        break;
-      }
-    }
-  }
-
-  // feat_grad: the second warp of the strip hands its partial sums over
-  float *fgs = s_fg + ((size_t)(col * kStripV + v) * kFgPitch + hc * (C / 2));
-  if (part == 1) {
-#pragma unroll
-    for (int q = 0; q < Q; ++q) *reinterpret_cast<float4 *>(fgs + 4 * q) = fg[q];
-  }
-  __syncthreads();
-  if (part == 0 && pix_ok) {
-    float4 *dst = reinterpret_cast<float4 *>(p.feat_grad + pixel * C + (size_t)hc * (C / 2));
-#pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      const float4 o = *reinterpret_cast<const float4 *>(fgs + 4 * q);
-      st_stream_f4(dst + q, make_float4(fg[q].x + o.x, fg[q].y + o.y, fg[q].z + o.z, fg[q].w + o.w));
-    }
-  }
-  for (int idx = tid; idx < D * kStripV; idx += 64 * kStripCols) {
-    const int d = idx >> 4, i = idx & 15, vv = v0 + i;
-    if (vv >= g.H) continue;
-    float c[kStripCols];
-#pragma unroll
-    for (int k = 0; k < kStripCols; ++k)
-      c[k] = (s_kept[k * D + d] >> i) & 1u ? s_w[(k * D + d) * kStripV + i] : 0.f;
-    float *dst = p.depth_grad + ((size_t)(img * D + d) * g.HW + (size_t)vv * g.W + u0);
-    if (p.vec4) {
-      st_stream_f4(reinterpret_cast<float4 *>(dst), make_float4(c[0], c[1], c[2], c[3]));
-    } else {
-#pragma unroll
-      for (int k = 0; k < kStripCols; ++k)
-        if (u0 + k < g.W) st_stream_f32(dst + k, c[k]);
-    }
+    for (int q = 0; q < CPL; ++q) dst[4 * q] = a[q];
   }
 }
 
@@ -692,8 +715,6 @@ __global__ void __launch_bounds__(64 * kStripCols, 2) k_bwd_strips(BwdStripsPara
 static bool strips_channels_ok(int C) { return C == 64 || C == 80 || C == 128; }
 static bool strips_bwd_channels_ok(int C) { return C == 64 || C == 80; }
 
-static size_t slab_bytes(const StripGeom &g) { return (size_t)kStripCols * g.D * kStripV * 4; }
-
 template <typename K>
 static int set_smem(K kernel, size_t smem) {
   if (smem > 48 * 1024)
@@ -701,17 +722,19 @@ static int set_smem(K kernel, size_t smem) {
   return RCB_OK;
 }
 
+static size_t strips_smem(const StripGeom &g) { return (size_t)g.group_cap * (kStripV * 4 + 4); }
+
 template <typename FeatT, int CPL>
-static int launch_fwd_strips_t(const FwdStripsParams &p, cudaStream_t s) {
-  const size_t smem = slab_bytes(p.g) + (size_t)kStripCols * p.g.ent_cap * 4;
+static int launch_fwd_strips_t(const StripsParams &p, cudaStream_t s) {
+  const size_t smem = strips_smem(p.g);
   int rc = set_smem(k_fwd_strips<FeatT, CPL>, smem);
   if (rc != RCB_OK) return rc;
-  RCB_CUDA_TRY(launch_pdl(k_fwd_strips<FeatT, CPL>, (unsigned)(p.g.n_img * p.g.VC * p.g.UG), 64 * kStripCols, smem, s, p));
+  RCB_CUDA_TRY(launch_pdl(k_fwd_strips<FeatT, CPL>, (unsigned)p.g.n_groups, 32 * kStripCols, smem, s, p));
   return RCB_OK;
 }
 
 template <typename FeatT>
-static int launch_fwd_strips(const FwdStripsParams &p, int C, cudaStream_t s) {
+static int launch_fwd_strips(const StripsParams &p, int C, cudaStream_t s) {
   switch (C) {
     case 64: return launch_fwd_strips_t<FeatT, 4>(p, s);
     case 80: return launch_fwd_strips_t<FeatT, 5>(p, s);
@@ -721,11 +744,8 @@ static int launch_fwd_strips(const FwdStripsParams &p, int C, cudaStream_t s) {
 
 template <int CPL>
 static int launch_combine_t(const CombineParams &p, int B, bool spread, cudaStream_t s) {
-  const size_t smem = p.layout == RCB_LAYOUT_B_C_CELLS ? (size_t)16 * CPL * (kCombineCells + 1) * 4 : 0;
   auto kernel = spread ? k_bwd_spread<CPL> : k_fwd_combine<CPL>;
-  int rc = set_smem(kernel, smem);
-  if (rc != RCB_OK) return rc;
-  RCB_CUDA_TRY(launch_pdl(kernel, (unsigned)(B * p.tiles_per_sample), 256, smem, s, p));
+  RCB_CUDA_TRY(launch_pdl(kernel, (unsigned)(B * p.tiles_per_sample), 256, 0, s, p));
   return RCB_OK;
 }
 
@@ -737,24 +757,31 @@ static int launch_combine(const CombineParams &p, int B, int C, bool spread, cud
   }
 }
 
-template <typename FeatT, int Q>
-static int launch_bwd_strips_t(const BwdStripsParams &p, cudaStream_t s) {
-  constexpr int C = 8 * Q;
-  const size_t smem = slab_bytes(p.g) + (size_t)kStripCols * p.g.ent_cap * 4 + (size_t)2 * kStripCols * C * 4 +
-                      (size_t)kStripCols * kStripV * (C + 4) * 4 + (size_t)kStripCols * p.g.D * 4;
-  int rc = set_smem(k_bwd_strips<FeatT, Q>, smem);
+template <typename FeatT, int CPL>
+static int launch_bwd_strips_t(const StripsParams &p, cudaStream_t s) {
+  const size_t smem = strips_smem(p.g);
+  int rc = set_smem(k_bwd_strips<FeatT, CPL>, smem);
   if (rc != RCB_OK) return rc;
-  RCB_CUDA_TRY(launch_pdl(k_bwd_strips<FeatT, Q>, (unsigned)(p.g.n_img * p.g.VC * p.g.UG), 64 * kStripCols, smem, s, p));
+  RCB_CUDA_TRY(launch_pdl(k_bwd_strips<FeatT, CPL>, (unsigned)p.g.n_groups, 32 * kStripCols, smem, s, p));
   return RCB_OK;
 }
 
 template <typename FeatT>
-static int launch_bwd_strips(const BwdStripsParams &p, int C, cudaStream_t s) {
-  return C == 64 ? launch_bwd_strips_t<FeatT, 8>(p, s) : launch_bwd_strips_t<FeatT, 10>(p, s);
+static int launch_bwd_strips(const StripsParams &p, int C, cudaStream_t s) {
+  return C == 64 ? launch_bwd_strips_t<FeatT, 4>(p, s) : launch_bwd_strips_t<FeatT, 5>(p, s);
 }
 
 static bool geom_matches(const rcb_pool_desc *d, const StripGeom &g) {
   return d->n_depth == g.n_list && d->n_pixels == g.n_img * g.HW && d->B * d->Z * d->Y * d->X == g.n_cells;
+}
+
+static StripsParams strips_params(const StripGeom &g, const PlanView &pv, const float *depth, const void *feat,
+                                  float *rows) {
+  StripsParams p;
+  p.depth = depth, p.feat = feat, p.status = pv.status, p.nseg = pv.nseg, p.label = pv.label, p.seg_dst = pv.seg_dst;
+  p.rows = rows, p.depth_grad = nullptr, p.feat_grad = nullptr, p.g = g;
+  p.vec4 = 0;
+  return p;
 }
 
 }  // namespace rcb
@@ -784,31 +811,30 @@ extern "C" int rcb_strip_plan_build(const rcb_strip_desc *d, const int *point_ce
   DeviceGuard guard(device);
   if (guard.err) return guard.err;
   cudaStream_t s = (cudaStream_t)stream;
-  RCB_CUDA_TRY(cudaMemsetAsync(pv.status, 0, 256, s));
-  RCB_CUDA_TRY(cudaMemsetAsync(pv.cell_nseg, 0, (size_t)g.n_cells * 4, s));
+  RCB_CUDA_TRY(cudaMemsetAsync(plan, 0, pv.zero_bytes, s));  // status, segment counts per cell and per block
   StripPlanParams p;
-  p.point_cell = point_cell, p.cell_start = cell_start, p.status = pv.status, p.info = pv.info, p.ent = pv.ent;
-  p.cell_nseg = pv.cell_nseg, p.raw = pv.raw, p.g = g;
+  p.point_cell = point_cell, p.cell_start = cell_start, p.status = pv.status, p.nseg = pv.nseg, p.label = pv.label;
+  p.cell_nseg = pv.cell_nseg, p.block_sum = pv.block_sum, p.raw = pv.raw, p.g = g;
   p.vec4 = (g.W % 4) == 0 && (((uintptr_t)point_cell) % 16) == 0;
-  const size_t smem = slab_bytes(g) + (size_t)kStripCols * g.ent_cap * 8;
+  const size_t smem = (size_t)kStripCols * g.D * kStripV * 4 + (size_t)kStripCols * g.ent_cap * 8;
   int rc = set_smem(k_strip_plan, smem);
   if (rc != RCB_OK) return rc;
-  k_strip_plan<<<(unsigned)(g.n_img * g.VC * g.UG), 32 * kStripCols, smem, s>>>(p);
+  k_strip_plan<<<(unsigned)g.n_groups, 32 * kStripCols, smem, s>>>(p);
   RCB_LAUNCH_CHECK();
-  RCB_CUDA_TRY(launch_pdl(k_cellseg_sort, (unsigned)ceil_div(g.n_cells, 256), 256, 0, s, (const int *)pv.cell_nseg,
-                          cell_start, (const int *)pv.raw, pv.list, g.n_cells, pv.status));
+  RCB_CUDA_TRY(launch_pdl(k_cellseg_index, (unsigned)ceil_div(g.n_cells, kIndexBlock), kIndexBlock, 0, s,
+                          (const int *)pv.cell_nseg, (const int *)pv.block_sum, cell_start, (const int *)pv.raw,
+                          pv.seg_start, pv.seg_dst, g.n_cells, pv.status));
   return RCB_OK;
 }
 
 extern "C" int rcb_bev_pool_v2_fwd_strips(const rcb_pool_desc *d, const rcb_strip_desc *sd, const void *plan,
-                                          const int *cell_start, const float *depth, const void *feat,
-                                          float *out, void *rows, size_t rows_bytes, int device,
-                                          rcb_stream_t stream) {
+                                          const float *depth, const void *feat, float *out, void *rows,
+                                          size_t rows_bytes, int device, rcb_stream_t stream) {
   int rc = check_pool_desc(d);
   if (rc != RCB_OK) return rc;
   StripGeom g;
   if (!make_geom(sd, &g) || !strips_channels_ok(d->C) || !geom_matches(d, g)) return RCB_ERR_UNSUPPORTED;
-  if (!plan || !cell_start || !depth || !feat || !out || !rows) return RCB_ERR_ARG;
+  if (!plan || !depth || !feat || !out || !rows) return RCB_ERR_ARG;
   if (rows_bytes < (size_t)g.n_strips * g.seg_cap * d->C * 4) return RCB_ERR_WORKSPACE;
   const int elem = d->feat_dtype == RCB_DTYPE_F32 ? 4 : 2;
   if ((((uintptr_t)feat) % elem) != 0 || (((uintptr_t)rows) % 16) != 0) return RCB_ERR_ALIGN;
@@ -816,10 +842,7 @@ extern "C" int rcb_bev_pool_v2_fwd_strips(const rcb_pool_desc *d, const rcb_stri
   if (guard.err) return guard.err;
   cudaStream_t s = (cudaStream_t)stream;
   PlanView pv = plan_view(g, const_cast<void *>(plan));
-  FwdStripsParams p;
-  p.depth = depth, p.feat = feat, p.status = pv.status, p.info = pv.info, p.ent = pv.ent;
-  p.rows = static_cast<float *>(rows), p.g = g;
-  p.vec4 = (g.W % 4) == 0 && (((uintptr_t)depth) % 16) == 0;
+  StripsParams p = strips_params(g, pv, depth, feat, static_cast<float *>(rows));
   switch (d->feat_dtype) {
     case RCB_DTYPE_F32: rc = launch_fwd_strips<float>(p, d->C, s); break;
     case RCB_DTYPE_BF16: rc = launch_fwd_strips<__nv_bfloat16>(p, d->C, s); break;
@@ -827,39 +850,37 @@ extern "C" int rcb_bev_pool_v2_fwd_strips(const rcb_pool_desc *d, const rcb_stri
   }
   if (rc != RCB_OK) return rc;
   CombineParams c;
-  c.status = pv.status, c.cell_nseg = pv.cell_nseg, c.cell_start = cell_start, c.list = pv.list;
+  c.status = pv.status, c.seg_start = pv.seg_start;
   c.rows = static_cast<float *>(rows), c.out = out;
   c.cps = d->Z * d->Y * d->X, c.tiles_per_sample = ceil_div(c.cps, kCombineCells), c.layout = d->layout;
   return launch_combine(c, d->B, d->C, false, s);
 }
 
 extern "C" int rcb_bev_pool_v2_bwd_strips(const rcb_pool_desc *d, const rcb_strip_desc *sd, const void *plan,
-                                          const int *cell_start, const float *out_grad, const float *depth,
-                                          const void *feat, float *depth_grad, float *feat_grad, void *rows,
-                                          size_t rows_bytes, int device, rcb_stream_t stream) {
+                                          const float *out_grad, const float *depth, const void *feat,
+                                          float *depth_grad, float *feat_grad, void *rows, size_t rows_bytes,
+                                          int device, rcb_stream_t stream) {
   int rc = check_pool_desc(d);
   if (rc != RCB_OK) return rc;
   StripGeom g;
   if (!make_geom(sd, &g) || !strips_bwd_channels_ok(d->C) || !geom_matches(d, g)) return RCB_ERR_UNSUPPORTED;
-  if (!plan || !cell_start || !out_grad || !depth || !feat || !depth_grad || !feat_grad || !rows) return RCB_ERR_ARG;
+  if (!plan || !out_grad || !depth || !feat || !depth_grad || !feat_grad || !rows) return RCB_ERR_ARG;
   if (rows_bytes < (size_t)g.n_strips * g.seg_cap * d->C * 4) return RCB_ERR_WORKSPACE;
   const int elem = d->feat_dtype == RCB_DTYPE_F32 ? 4 : 2;
-  if ((((uintptr_t)feat) % (4 * elem)) != 0 || (((uintptr_t)rows) % 16) != 0 || (((uintptr_t)feat_grad) % 16) != 0)
-    return RCB_ERR_ALIGN;
+  if ((((uintptr_t)feat) % elem) != 0 || (((uintptr_t)rows) % 16) != 0) return RCB_ERR_ALIGN;
   DeviceGuard guard(device);
   if (guard.err) return guard.err;
   cudaStream_t s = (cudaStream_t)stream;
   PlanView pv = plan_view(g, const_cast<void *>(plan));
   CombineParams c;
-  c.status = pv.status, c.cell_nseg = pv.cell_nseg, c.cell_start = cell_start, c.list = pv.list;
+  c.status = pv.status, c.seg_start = pv.seg_start;
   c.rows = static_cast<float *>(rows), c.out = const_cast<float *>(out_grad);
   c.cps = d->Z * d->Y * d->X, c.tiles_per_sample = ceil_div(c.cps, kCombineCells), c.layout = d->layout;
   rc = launch_combine(c, d->B, d->C, true, s);
   if (rc != RCB_OK) return rc;
-  BwdStripsParams p;
-  p.depth = depth, p.feat = feat, p.status = pv.status, p.info = pv.info, p.ent = pv.ent;
-  p.rows = static_cast<const float *>(rows), p.depth_grad = depth_grad, p.feat_grad = feat_grad, p.g = g;
-  p.vec4 = (g.W % 4) == 0 && (((uintptr_t)depth) % 16) == 0 && (((uintptr_t)depth_grad) % 16) == 0;
+  StripsParams p = strips_params(g, pv, depth, feat, static_cast<float *>(rows));
+  p.depth_grad = depth_grad, p.feat_grad = feat_grad;
+  p.vec4 = (g.W % 4) == 0 && (((uintptr_t)depth_grad) % 16) == 0;
   switch (d->feat_dtype) {
     case RCB_DTYPE_F32: return launch_bwd_strips<float>(p, d->C, s);
     case RCB_DTYPE_BF16: return launch_bwd_strips<__nv_bfloat16>(p, d->C, s);

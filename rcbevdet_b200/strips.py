@@ -75,7 +75,7 @@ def forward(plan, pool_desc, depth, rows_feat, out):
     ws = plan.rows(pool_desc.C)
     dev = out.device
     _lib.check(_lib.lib().rcb_bev_pool_v2_fwd_strips(
-        ctypes.byref(pool_desc), ctypes.byref(plan.desc), _lib.ptr(plan.buf), _lib.ptr(plan.cell_start),
+        ctypes.byref(pool_desc), ctypes.byref(plan.desc), _lib.ptr(plan.buf),
         _lib.ptr(depth), _lib.ptr(rows_feat), _lib.ptr(out), _lib.ptr(ws), ws.numel(), dev.index,
         _lib.stream_ptr(dev)), "rcb_bev_pool_v2_fwd_strips")
 
@@ -84,6 +84,6 @@ def backward(plan, pool_desc, out_grad, depth, rows_feat, depth_grad, feat_grad)
     ws = plan.rows(pool_desc.C)
     dev = out_grad.device
     _lib.check(_lib.lib().rcb_bev_pool_v2_bwd_strips(
-        ctypes.byref(pool_desc), ctypes.byref(plan.desc), _lib.ptr(plan.buf), _lib.ptr(plan.cell_start),
+        ctypes.byref(pool_desc), ctypes.byref(plan.desc), _lib.ptr(plan.buf),
         _lib.ptr(out_grad), _lib.ptr(depth), _lib.ptr(rows_feat), _lib.ptr(depth_grad), _lib.ptr(feat_grad),
         _lib.ptr(ws), ws.numel(), dev.index, _lib.stream_ptr(dev)), "rcb_bev_pool_v2_bwd_strips")

@@ -46,10 +46,11 @@ def run(B, grid, input_size, depth_cfg, C=80, aug=None, layout=_lib.LAYOUT_B_C_C
     out_ref = torch.empty(shape, device=dev)
     bp.pool_forward(d, depth, rows, r.ranks_depth, r.ranks_feat, r.ranks_bev, None, None, r.cell_start, out_ref)
     sp = strips.build(r.point_cell, r.cell_start, B * N, D, H, W, r.n_cells)
-    info = sp.buf[256:256 + 16 * B * N * ((H + 15) // 16) * W].view(torch.int32).view(-1, 4)
+    al = lambda v: (v + 255) // 256 * 256
+    off = 256 + al(r.n_cells * 4) + al((r.n_cells + 255) // 256 * 4)
+    nseg = sp.buf[off:off + 4 * B * N * ((H + 15) // 16) * W].view(torch.int32)
     print(f"B={B} {input_size} D={D} H={H} W={W} C={C} aug={aug} layout={layout} {dtype}: status={sp.status()} "
-          f"entries={int(info[:, 0].sum())} (max {int(info[:, 0].max())}) segments={int(info[:, 1].sum())} "
-          f"(max {int(info[:, 1].max())}) kept={int(r.counts[0])}")
+          f"segments={int(nseg.sum())} (max {int(nseg.max())}) kept={int(r.counts[0])}")
     out = torch.full(shape, float("nan"), device=dev)
     strips.forward(sp, d, depth, rows, out)
     torch.cuda.synchronize()
@@ -90,6 +91,9 @@ def run(B, grid, input_size, depth_cfg, C=80, aug=None, layout=_lib.LAYOUT_B_C_C
 
 if __name__ == "__main__":
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    if len(sys.argv) > 2 and sys.argv[2] == "one":      # the B-sample R50 case only (for ncu)
+        aug = int(sys.argv[3]) if len(sys.argv) > 3 else None
+        sys.exit(0 if run(B, rig.R50_GRID, rig.R50_INPUT, rig.R50_GRID["depth"], aug=aug, time=True) else 1)
     ok = True
     ok &= run(1, rig.R50_GRID, (64, 176), (1.0, 60.0, 4.0))
     ok &= run(2, rig.R50_GRID, (128, 352), (1.0, 60.0, 2.0), aug=3)
