@@ -19,5 +19,6 @@ from .view_pool import voxel_pooling_v2, voxel_pooling_v2_from_calib  # noqa: F4
 from .radar import PointPillarsScatterRCS, radar_rcs_scatter  # noqa: F401
 from .temporal import gen_grid_transform, shift_feature  # noqa: F401
 from .lift import depth_context_split, lss_view_transform  # noqa: F401
+from . import strips  # noqa: F401  (strip kernels: strips.set_mode("auto" | "on" | "off"))
 
 __version__ = "0.1.0"

@@ -18,7 +18,7 @@ import ctypes
 
 import torch
 
-from . import _lib, plan as _plan
+from . import _lib, plan as _plan, strips as _strips
 
 __all__ = ["bev_pool_v2", "TRTBEVPoolv2", "QuickCumsumCuda"]
 
@@ -110,8 +110,12 @@ def _forward(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, in
     B, Z, Y, X, C = desc.B, desc.Z, desc.Y, desc.X, desc.C
     shape = (B, C, Z, Y, X) if layout == _lib.LAYOUT_B_C_CELLS else (B, Z, Y, X, C)
     out = torch.empty(shape, dtype=torch.float32, device=dev)
-    pool_forward(desc, depth, rows, ranks_depth, ranks_feat, ranks_bev, interval_lengths, interval_starts,
-                 plan.cell_start if plan.sorted_cells else None, out)
+    sp = _strips.for_forward(plan, desc)
+    if sp is not None:
+        _strips.forward(sp, desc, depth, rows, out)
+    else:
+        pool_forward(desc, depth, rows, ranks_depth, ranks_feat, ranks_bev, interval_lengths, interval_starts,
+                     plan.cell_start if plan.sorted_cells else None, out)
     saved = (depth, rows, ranks_depth, ranks_feat, ranks_bev)
     return out, saved, desc, plan
 
@@ -139,6 +143,12 @@ def _backward(out_grad, saved, desc, plan, feat_shape, feat_dtype, depth_shape, 
     desc = bwd_desc
     depth_grad = torch.empty(depth.shape, dtype=torch.float32, device=dev)
     feat_grad = torch.empty(rows.shape, dtype=torch.float32, device=dev)
+    sp = _strips.for_backward(plan, desc)
+    if sp is not None:
+        _strips.backward(sp, desc, out_grad, depth, rows, depth_grad, feat_grad)
+        depth_grad, feat_grad = depth_grad.view(depth_shape), feat_grad.view(feat_shape)
+        return (depth_grad if depth_dtype == torch.float32 else depth_grad.to(depth_dtype),
+                feat_grad if feat_dtype == torch.float32 else feat_grad.to(feat_dtype))
     lib = _lib.lib()
     ws_bytes = lib.rcb_pool_bwd_workspace_bytes(ctypes.byref(desc))
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)

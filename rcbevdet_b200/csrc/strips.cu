@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(32 * kStripCols, CPL <= 5 ? 4 : 2) k_fwd_strip
   const int b0 = c.at(col), n = c.at(col + 1) - b0;
   const float *wrow = s_W + (size_t)b0 * kStripV + 8 * h;
   const int *dsts = s_dst + b0;
-#pragma unroll 2
+#pragma unroll 4
   for (int sg = 0; sg < n; ++sg) {
     const float4 wa = *reinterpret_cast<const float4 *>(wrow + sg * kStripV);
     const float4 wb = *reinterpret_cast<const float4 *>(wrow + sg * kStripV + 4);

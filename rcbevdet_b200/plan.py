@@ -25,7 +25,8 @@ class PoolPlan:
     unless SORTED_CELLS).  point_cell: int32 [n_depth] BEV cell of each depth element, -1 if
     unused (None unless STRUCTURED).  D / HW describe the frustum when STRUCTURED."""
 
-    __slots__ = ("flags", "cell_start", "point_cell", "D", "HW", "n_cells", "n_depth", "keys", "hold", "ranks")
+    __slots__ = ("flags", "cell_start", "point_cell", "D", "HW", "n_cells", "n_depth", "keys", "hold", "ranks",
+                 "strips", "uses")
 
     def __init__(self, flags, cell_start, point_cell, D, HW, n_cells, n_depth, keys=None, hold=None,
                  ranks=None):
@@ -42,6 +43,10 @@ class PoolPlan:
         # arrive as int64 / strided views these are converted ONCE and kept here, so the cache hits
         # on the caller's own tensors instead of on a fresh copy per call
         self.ranks = ranks
+        # second-level plan of the strip kernels (rcbevdet_b200/strips.py): None = not built yet,
+        # False = built and refused (or geometry outside the envelope); `uses` counts forwards
+        self.strips = None
+        self.uses = 0
 
     @property
     def sorted_cells(self):

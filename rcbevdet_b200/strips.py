@@ -10,6 +10,7 @@ forward / backward that runs on those ranks.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -18,16 +19,31 @@ from . import _lib
 FWD_CHANNELS = (64, 80, 128)
 BWD_CHANNELS = (64, 80)
 
+# Which pooling kernels bev_pool_v2 / voxel_pooling_v2 run on structured ranks:
+#   "auto" (default): the forward switches to the strip kernels from the SECOND forward that sees the
+#           same ranks (cached ranks: the reference's accelerate mode, init_acceleration_v2 -- the plan
+#           costs about as much as one forward, so it pays from the second use on); backward unchanged
+#   "on"  : strip kernels for forward and backward, plan built at first use
+#   "off" : cell-/pixel-stationary kernels only
+# Environment: RCB_STRIPS=auto|on|off.
+MODE = os.environ.get("RCB_STRIPS", "auto").lower()
+
+
+def set_mode(mode):
+    global MODE
+    if mode not in ("auto", "on", "off"):
+        raise ValueError("mode must be 'auto', 'on' or 'off'")
+    MODE = mode
+
 
 class StripPlan:
     """desc: rcb_strip_desc; buf: the device plan buffer; status(): 0 when the strip kernels may run."""
 
-    __slots__ = ("desc", "buf", "cell_start", "_status", "_rows")
+    __slots__ = ("desc", "buf", "cell_start", "_status")
 
     def __init__(self, desc, buf, cell_start):
         self.desc, self.buf, self.cell_start = desc, buf, cell_start
         self._status = None
-        self._rows = {}
 
     def status_tensor(self):
         return self.buf[:4].view(torch.int32)
@@ -39,14 +55,11 @@ class StripPlan:
         return self._status
 
     def rows(self, C):
-        """Scratch for the segment rows (allocated once per channel count, reused by every call on
-        the same stream)."""
-        ws = self._rows.get(C)
-        if ws is None:
-            n = _lib.lib().rcb_strip_rows_bytes(ctypes.byref(self.desc), C)
-            ws = torch.empty(n, dtype=torch.uint8, device=self.buf.device)
-            self._rows[C] = ws
-        return ws
+        """Scratch for the segment rows of one call: reserved address space from torch's caching
+        allocator (stream-ordered, so calls on different streams do not share it); only the rows of
+        existing segments are ever touched."""
+        n = _lib.lib().rcb_strip_rows_bytes(ctypes.byref(self.desc), C)
+        return torch.empty(n, dtype=torch.uint8, device=self.buf.device)
 
 
 def supported(n_img, D, H, W, n_cells):
@@ -87,3 +100,33 @@ def backward(plan, pool_desc, out_grad, depth, rows_feat, depth_grad, feat_grad)
         ctypes.byref(pool_desc), ctypes.byref(plan.desc), _lib.ptr(plan.buf),
         _lib.ptr(out_grad), _lib.ptr(depth), _lib.ptr(rows_feat), _lib.ptr(depth_grad), _lib.ptr(feat_grad),
         _lib.ptr(ws), ws.numel(), dev.index, _lib.stream_ptr(dev)), "rcb_bev_pool_v2_bwd_strips")
+
+
+def _for_plan(plan, desc):
+    """The StripPlan of a PoolPlan (built on first request; one 4-byte read-back of its status), or None
+    when the strip kernels cannot take these ranks."""
+    if plan.strips is None:
+        ok = (plan.structured and plan.sorted_cells and desc.D > 0 and desc.H > 0 and desc.HW > 0
+              and desc.HW % desc.H == 0 and desc.n_pixels % desc.HW == 0
+              and desc.n_pixels * desc.D == desc.n_depth)
+        if ok and torch.cuda.is_current_stream_capturing():
+            return None                                     # the status read-back cannot be captured
+        sp = build(plan.point_cell, plan.cell_start, desc.n_pixels // desc.HW, desc.D, desc.H,
+                   desc.HW // desc.H, plan.n_cells) if ok else None
+        plan.strips = sp if (sp is not None and sp.status() == 0) else False
+    return plan.strips or None
+
+
+def for_forward(plan, desc):
+    if MODE == "off" or desc.C not in FWD_CHANNELS:
+        return None
+    plan.uses += 1
+    if MODE == "auto" and plan.uses < 2 and plan.strips is None:
+        return None
+    return _for_plan(plan, desc)
+
+
+def for_backward(plan, desc):
+    if MODE != "on" or desc.C not in BWD_CHANNELS:
+        return None
+    return _for_plan(plan, desc)

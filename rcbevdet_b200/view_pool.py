@@ -13,7 +13,7 @@ import ctypes
 
 import torch
 
-from . import _lib, bev_pool as _bp, plan as _plan
+from . import _lib, bev_pool as _bp, plan as _plan, strips as _strips
 from .prepare import prepare_async, prepare_from_calib_async
 
 
@@ -36,11 +36,15 @@ class _ViewPool(torch.autograd.Function):
             raise ValueError("depth / feat shapes do not match the frustum that `coor` describes")
         shape = (prepared.B, gz, gy, gx, C) if channels_last else (prepared.B, C, gz, gy, gx)
         out = torch.empty(shape, dtype=torch.float32, device=dev)
-        _bp.pool_forward(d, depth_c, rows, prepared.ranks_depth, prepared.ranks_feat, prepared.ranks_bev, None, None,
-                         prepared.cell_start, out)
-        ctx.save_for_backward(depth_c, rows, prepared.ranks_depth, prepared.ranks_feat, prepared.ranks_bev)
         plan = _plan.PoolPlan(_lib.PLAN_ALL, prepared.cell_start, prepared.point_cell, prepared.D,
                               prepared.HW, prepared.n_cells, prepared.P)
+        sp = _strips.for_forward(plan, d)          # "on" only: the plan of this chain is never reused
+        if sp is not None:
+            _strips.forward(sp, d, depth_c, rows, out)
+        else:
+            _bp.pool_forward(d, depth_c, rows, prepared.ranks_depth, prepared.ranks_feat, prepared.ranks_bev, None,
+                             None, prepared.cell_start, out)
+        ctx.save_for_backward(depth_c, rows, prepared.ranks_depth, prepared.ranks_feat, prepared.ranks_bev)
         ctx.rcb = (d, plan, tuple(feat.shape), feat.dtype, tuple(depth.shape), depth.dtype)
         return out.permute(0, 4, 1, 2, 3) if channels_last else out   # logically (B, C, Z, Y, X) either way
 
