@@ -316,6 +316,53 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         return e0.elapsed_time(e1) / n
 
+    def strips_variant(n=50):
+        """The strip kernels (csrc/strips.cu, opt-in: strips.set_mode) on the same inputs: plan build,
+        forward and backward with the plan cached -- what cached ranks (the reference's accelerate mode)
+        pay per call.  Outputs checked against the cell-/pixel-stationary kernels before timing."""
+        from rcbevdet_b200 import strips
+        coor, depth, feat, out_grad = sets[0]
+        rows = bp.feat_rows(feat.permute(0, 1, 3, 4, 2))
+        prepared = prepare_async(coor, lo, iv, sz)
+        d = _lib.PoolDesc()
+        d.n_points, d.n_intervals, d.C = prepared.P, 0, C
+        d.B, d.Z, d.Y, d.X = B, 1, 128, 128
+        d.n_depth, d.n_pixels, d.D, d.HW, d.H = depth.numel(), rows.shape[0], prepared.D, prepared.HW, prepared.H
+        d.layout, d.feat_dtype, d.flags = _lib.LAYOUT_B_C_CELLS, _lib.DTYPE_F32, _lib.PLAN_ALL
+        n_img, W_ = rows.shape[0] // prepared.HW, prepared.HW // prepared.H
+
+        def build():
+            return strips.build(prepared.point_cell, prepared.cell_start, n_img, prepared.D, prepared.H, W_, prepared.n_cells)
+
+        sp = build()
+        if sp is None or sp.status() != 0:
+            return {"status": None if sp is None else sp.status()}
+        ref = torch.empty((B, C, 1, 128, 128), dtype=torch.float32, device=dev)
+        bp.pool_forward(d, depth, rows, prepared.ranks_depth, prepared.ranks_feat, prepared.ranks_bev, None, None,
+                        prepared.cell_start, ref)
+        outs = [torch.empty_like(ref) for _ in range(4)]
+        dg, fg = torch.empty_like(depth), torch.empty_like(rows)
+        strips.forward(sp, d, depth, rows, outs[0])
+        err = float((outs[0] - ref).abs().max() / ref.abs().max())
+
+        def timed(fn):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for k in range(n + 5):
+                if k == 5:
+                    e0.record(stream)
+                fn(k)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            return round(e0.elapsed_time(e1) / n, 5)
+
+        return {"status": 0, "fwd_rel_err_vs_cells": err,
+                "plan_ms": timed(lambda k: build()),
+                "fwd_ms": timed(lambda k: strips.forward(sp, d, depth, rows, outs[k % 4])),
+                "bwd_ms": timed(lambda k: strips.backward(sp, d, out_grad, depth, rows, dg, fg)),
+                "note": "strip-stationary kernels with the plan cached (forward = strip pass + cell combine; "
+                        "backward = spread + strip pass, takes the (B,C,cells) gradient directly: no transpose); "
+                        "compare fwd_f32_rows_ms and stages_ms.og_rows + stages_ms.bwd"}
+
     variants = None
     if not args.profile:
         # the opt-in channels-last result (no transposed write, gradient consumed in place): same step,
@@ -336,6 +383,7 @@ def run_ours(args):
         variants = {"fwd_f32_rows_ms": round(fwd_only(rows32, _lib.DTYPE_F32), 5),
                     "fwd_bf16_rows_ms": round(fwd_only(rows32.bfloat16(), _lib.DTYPE_BF16), 5),
                     "step_channels_last_ms": round(step_cl_ms, 5),
+                    "strips": strips_variant(),
                     "note": "fwd_*: forward kernel alone, same plan, 4 rotating outputs (inputs L2-warm); "
                             "step_channels_last_ms: the whole step with bev_pool_v2(..., channels_last=True) "
                             "semantics (rows written directly, channels-last out_grad used in place)"}

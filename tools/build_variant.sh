@@ -7,7 +7,7 @@ cd "$(dirname "$0")/.."
 NAME=$1; shift
 OUT=rcbevdet_b200/lib/variants; mkdir -p $OUT /tmp/rcbv_$NAME
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo --expt-extended-lambda -Xcompiler -fPIC --fmad=true --prec-div=true --ftz=false -Xptxas -v $*"
-for f in api prepare prepare_lsd pool_plan pool_fwd pool_fwd_cells pool_bwd layout radar bev_shift depth_context trt_plugin; do
+for f in api prepare prepare_lsd pool_plan pool_fwd pool_fwd_cells pool_bwd strips layout radar bev_shift depth_context trt_plugin; do
   nvcc $FLAGS -c rcbevdet_b200/csrc/$f.cu -o /tmp/rcbv_$NAME/$f.o > /tmp/rcbv_$NAME/$f.log 2>&1 &
 done
 wait

