@@ -33,7 +33,7 @@
 //
 // Nothing here uses float atomics; integer atomics only hand out list slots and count, and the
 // lists are sorted before rows are assigned, so every output is bit-reproducible.  Inputs the plan
-// cannot hold (more segments per strip / per group of four strips than reserved, which needs cells
+// cannot hold (more segments per strip / per group of eight strips than reserved, which needs cells
 // scattered at random along a column) raise the plan's status word: every kernel here then exits at
 // once and the caller runs the cell-/pixel-stationary kernels (pool_fwd_cells.cu, pool_bwd.cu).
 #include "common.cuh"
@@ -41,7 +41,8 @@
 namespace rcb {
 
 constexpr int kStripV = 16;    // pixels per strip
-constexpr int kStripCols = 4;  // adjacent image columns per CTA (16-byte runs of depth / point_cell)
+constexpr int kStripCols = 8;  // adjacent image columns per CTA: 32-byte runs of depth / point_cell = whole sectors
+constexpr int kGroupPix = kStripV * kStripCols;  // (pixel, column) pairs of a CTA per depth bin
 constexpr int kCombineCells = 64;
 constexpr int kIndexBlock = 256;  // cells per CTA of k_cellseg_index
 constexpr int kNoLabel = 0xffff;
@@ -51,7 +52,7 @@ struct StripGeom {
   int VC;  // strips per image column
   int UG;  // column groups per image row
   int seg_cap;    // segments a strip may have (stride of seg_dst)
-  int group_cap;  // segments the four strips of a CTA may have together (rows of W in shared memory)
+  int group_cap;  // segments the strips of a CTA may have together (rows of W in shared memory)
   int ent_cap;    // (cell, depth bin) entries a strip may have while the plan is built
   int n_strips, n_groups;
   int n_cells;
@@ -72,11 +73,11 @@ static bool make_geom(const rcb_strip_desc *d, StripGeom *g) {
   g->VC = ceil_div(d->H, kStripV), g->UG = ceil_div(d->W, kStripCols);
   g->ent_cap = next_pow2(4 * d->D);
   g->seg_cap = (int)align_up((size_t)3 * d->D, 8);
-  g->group_cap = 768;  // rows of W a CTA can hold: 52 KB of shared memory, four CTAs per SM
+  g->group_cap = 1536;  // rows of W a CTA can hold: 96 KB of shared memory, two CTAs of eight warps per SM
   const long long strips = (long long)d->n_img * g->VC * d->W;
   const long long groups = (long long)d->n_img * g->VC * g->UG;
   const long long points = (long long)d->n_img * d->D * g->HW;
-  if (strips * g->seg_cap >= (1ll << 31) || points >= (1ll << 31) || groups * d->D * 64 >= (1ll << 31)) return false;
+  if (strips * g->seg_cap >= (1ll << 31) || points >= (1ll << 31) || groups * d->D * kGroupPix >= (1ll << 31)) return false;
   g->n_strips = (int)strips, g->n_groups = (int)groups, g->n_cells = d->n_cells, g->n_list = (int)points;
   return true;
 }
@@ -87,7 +88,7 @@ struct PlanView {
   int *status;
   int *cell_nseg, *block_sum;
   int *nseg;                // [n_strips]
-  unsigned short *label;    // [n_groups][D][16][4]
+  unsigned short *label;    // [n_groups][D][16][kStripCols]
   int *seg_dst;             // [n_strips][seg_cap]
   int *seg_start, *raw;
   size_t zero_bytes, bytes;
@@ -102,7 +103,7 @@ static PlanView plan_view(const StripGeom &g, void *base) {
   v.block_sum = reinterpret_cast<int *>(p + off), off += align_up((size_t)ceil_div(g.n_cells, kIndexBlock) * 4, 256);
   v.zero_bytes = off;
   v.nseg = reinterpret_cast<int *>(p + off), off += align_up((size_t)g.n_strips * 4, 256);
-  v.label = reinterpret_cast<unsigned short *>(p + off), off += align_up((size_t)g.n_groups * g.D * 64 * 2, 256);
+  v.label = reinterpret_cast<unsigned short *>(p + off), off += align_up((size_t)g.n_groups * g.D * kGroupPix * 2, 256);
   v.seg_dst = reinterpret_cast<int *>(p + off), off += align_up((size_t)g.n_strips * g.seg_cap * 4, 256);
   v.seg_start = reinterpret_cast<int *>(p + off), off += align_up((size_t)(g.n_cells + 1) * 4, 256);
   v.raw = reinterpret_cast<int *>(p + off), off += align_up((size_t)g.n_list * 4, 256);
@@ -128,7 +129,7 @@ struct StripPlanParams {
   int vec4;
 };
 
-// One CTA per group of four adjacent strips, one warp per strip.  The strip's (cell, depth bin)
+// One CTA per group of eight adjacent strips, one warp per strip.  The strip's (cell, depth bin)
 // entries (distinct cells among the 16 pixels of a bin, with the pixel mask) are sorted by cell in
 // shared memory; runs of equal cell are the segments; every point gets its segment's index as label.
 __global__ void __launch_bounds__(32 * kStripCols) k_strip_plan(StripPlanParams p) {
@@ -146,12 +147,18 @@ __global__ void __launch_bounds__(32 * kStripCols) k_strip_plan(StripPlanParams 
 
   for (int idx = tid; idx < D * kStripV; idx += 32 * kStripCols) {
     const int d = idx >> 4, i = idx & 15, v = v0 + i;
-    int c[kStripCols] = {-1, -1, -1, -1};
+    int c[kStripCols];
+#pragma unroll
+    for (int k = 0; k < kStripCols; ++k) c[k] = -1;
     if (v < g.H) {
       const int *src = p.point_cell + ((size_t)(img * D + d) * g.HW + (size_t)v * g.W + u0);
       if (p.vec4) {
-        const int4 q = *reinterpret_cast<const int4 *>(src);
-        c[0] = q.x, c[1] = q.y, c[2] = q.z, c[3] = q.w;
+#pragma unroll
+        for (int k = 0; k < kStripCols; k += 4) {
+          if (u0 + k >= g.W) break;   // W % 4 == 0: a quad is inside the image or outside
+          const int4 q = *reinterpret_cast<const int4 *>(src + k);
+          c[k] = q.x, c[k + 1] = q.y, c[k + 2] = q.z, c[k + 3] = q.w;
+        }
       } else {
 #pragma unroll
         for (int k = 0; k < kStripCols; ++k)
@@ -254,17 +261,23 @@ __global__ void __launch_bounds__(32 * kStripCols) k_strip_plan(StripPlanParams 
   }
   if (lane == 0) s_segs[warp] = segs;
   __syncthreads();
-  if (tid == 0 && s_segs[0] + s_segs[1] + s_segs[2] + s_segs[3] > g.group_cap) atomicOr(p.status, 8);
+  if (tid == 0) {
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < kStripCols; ++k) sum += s_segs[k];
+    if (sum > g.group_cap) atomicOr(p.status, 8);
+  }
 
-  // labels leave as [group][d][pixel][column]: 8 bytes per (d, pixel), consecutive
-  unsigned short *lab = p.label + (size_t)blockIdx.x * D * 64;
+  // labels leave as [group][d][pixel][column]: 16 bytes per (d, pixel), consecutive
+  static_assert(kStripCols == 8, "label rows are written as one 128-bit word");
+  unsigned short *lab = p.label + (size_t)blockIdx.x * D * kGroupPix;
   for (int idx = tid; idx < D * kStripV; idx += 32 * kStripCols) {
-    ushort4 q;
-    q.x = (unsigned short)s_cells[(0 * D) * kStripV + idx];
-    q.y = (unsigned short)s_cells[(1 * D) * kStripV + idx];
-    q.z = (unsigned short)s_cells[(2 * D) * kStripV + idx];
-    q.w = (unsigned short)s_cells[(3 * D) * kStripV + idx];
-    reinterpret_cast<ushort4 *>(lab)[idx] = q;
+    unsigned q[kStripCols / 2];
+#pragma unroll
+    for (int k = 0; k < kStripCols; k += 2)
+      q[k / 2] = (unsigned)(unsigned short)s_cells[(k * D) * kStripV + idx] |
+                 ((unsigned)(unsigned short)s_cells[((k + 1) * D) * kStripV + idx] << 16);
+    reinterpret_cast<uint4 *>(lab)[idx] = make_uint4(q[0], q[1], q[2], q[3]);
   }
 }
 
@@ -365,7 +378,7 @@ struct StripsParams {
   int vec4;
 };
 
-// Shared prologue of the two strip kernels.  After it: s_W[row][16] holds, for the CTA's four strips
+// Shared prologue of the two strip kernels.  After it: s_W[row][16] holds, for the CTA's eight strips
 // back to back (strip k's segment s is row base[k] + s), the summed depth weight of every (segment,
 // pixel); s_dst[row] the workspace row of the segment.
 struct StripCta {
@@ -404,13 +417,13 @@ __device__ __forceinline__ void strip_prologue(const StripsParams &p, float *s_W
   // 32 that are loaded as a batch (one memory latency per chunk) and then walked in registers.  A run
   // belongs to the thread in whose half it starts; that thread follows it across the boundary.
   {
-    const int dh = tid >> 6, vk = tid & 63, v = vk >> 2, k = vk & 3;
+    const int dh = tid / kGroupPix, vk = tid % kGroupPix, v = vk / kStripCols, k = vk % kStripCols;
     if (c.v0 + v < g.H && c.u0 + k < g.W) {
       const int dlen = (D + 1) >> 1, d_begin = dh * dlen, d_end = min(D, d_begin + dlen);
-      const unsigned short *lab = p.label + (size_t)blockIdx.x * D * 64 + vk;
+      const unsigned short *lab = p.label + (size_t)blockIdx.x * D * kGroupPix + vk;
       const float *w = p.depth + ((size_t)c.img * D * g.HW + (size_t)(c.v0 + v) * g.W + c.u0 + k);
       float *wrow = s_W + (size_t)c.at(k) * kStripV + v;
-      int cur = d_begin > 0 ? (int)lab[(size_t)(d_begin - 1) * 64] : kNoLabel;
+      int cur = d_begin > 0 ? (int)lab[(size_t)(d_begin - 1) * kGroupPix] : kNoLabel;
       bool own = false;
       float acc = 0.f;
       for (int d0 = d_begin; d0 < d_end; d0 += 32) {
@@ -419,7 +432,7 @@ __device__ __forceinline__ void strip_prologue(const StripsParams &p, float *s_W
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const bool ok = d0 + i < d_end;
-          l[i] = ok ? (int)lab[(size_t)(d0 + i) * 64] : -1;
+          l[i] = ok ? (int)lab[(size_t)(d0 + i) * kGroupPix] : -1;
           x[i] = ok ? ld_stream_f32(w + (size_t)(d0 + i) * g.HW) : 0.f;
         }
 #pragma unroll
@@ -433,7 +446,7 @@ __device__ __forceinline__ void strip_prologue(const StripsParams &p, float *s_W
         }
       }
       if (own && cur != kNoLabel) {
-        for (int dd = d_end; dd < D && (int)lab[(size_t)dd * 64] == cur; ++dd) acc += ld_stream_f32(w + (size_t)dd * g.HW);
+        for (int dd = d_end; dd < D && (int)lab[(size_t)dd * kGroupPix] == cur; ++dd) acc += ld_stream_f32(w + (size_t)dd * g.HW);
         wrow[cur * kStripV] = acc;
       }
     }
@@ -467,7 +480,7 @@ __device__ __forceinline__ void load_strip_feat(const StripsParams &p, const Str
 }
 
 template <typename FeatT, int CPL>
-__global__ void __launch_bounds__(32 * kStripCols, CPL <= 5 ? 4 : 2) k_fwd_strips(StripsParams p) {
+__global__ void __launch_bounds__(32 * kStripCols, CPL <= 5 ? 2 : 1) k_fwd_strips(StripsParams p) {
   pdl_prologue();
   if (*p.status != 0) return;
   constexpr int C = 16 * CPL;
@@ -515,7 +528,7 @@ __global__ void __launch_bounds__(32 * kStripCols, CPL <= 5 ? 4 : 2) k_fwd_strip
 // j ends up with pixel (j >> 1) % 8), and overwrite the segment's W row once it has been consumed by
 // the feat_grad update.  At the end depth_grad[d][v] = W[label[d][v]][v], written coalesced.
 template <typename FeatT, int CPL>
-__global__ void __launch_bounds__(32 * kStripCols, 4) k_bwd_strips(StripsParams p) {
+__global__ void __launch_bounds__(32 * kStripCols, 2) k_bwd_strips(StripsParams p) {
   pdl_prologue();
   if (*p.status != 0) return;
   constexpr int C = 16 * CPL;
@@ -601,18 +614,23 @@ __global__ void __launch_bounds__(32 * kStripCols, 4) k_bwd_strips(StripsParams 
   }
   __syncthreads();
   const int D = g.D;
-  const ushort4 *lab = reinterpret_cast<const ushort4 *>(p.label + (size_t)blockIdx.x * D * 64);
+  const uint4 *lab = reinterpret_cast<const uint4 *>(p.label + (size_t)blockIdx.x * D * kGroupPix);
   for (int idx = tid; idx < D * kStripV; idx += 32 * kStripCols) {
     const int d = idx >> 4, i = idx & 15, vv = c.v0 + i;
     if (vv >= g.H) continue;
-    const ushort4 q = lab[idx];
-    const int l[kStripCols] = {q.x, q.y, q.z, q.w};
+    const uint4 q = lab[idx];
+    const unsigned qq[4] = {q.x, q.y, q.z, q.w};
     float o[kStripCols];
 #pragma unroll
-    for (int k = 0; k < kStripCols; ++k) o[k] = l[k] != kNoLabel ? s_W[(size_t)(c.base[k] + l[k]) * kStripV + i] : 0.f;
+    for (int k = 0; k < kStripCols; ++k) {
+      const int l = (qq[k >> 1] >> (16 * (k & 1))) & 0xffff;
+      o[k] = l != kNoLabel ? s_W[(size_t)(c.base[k] + l) * kStripV + i] : 0.f;
+    }
     float *dst = p.depth_grad + ((size_t)(c.img * D + d) * g.HW + (size_t)vv * g.W + c.u0);
     if (p.vec4) {
-      st_stream_f4(reinterpret_cast<float4 *>(dst), make_float4(o[0], o[1], o[2], o[3]));
+#pragma unroll
+      for (int k = 0; k < kStripCols; k += 4)
+        if (c.u0 + k < g.W) st_stream_f4(reinterpret_cast<float4 *>(dst + k), make_float4(o[k], o[k + 1], o[k + 2], o[k + 3]));
     } else {
 #pragma unroll
       for (int k = 0; k < kStripCols; ++k)
