@@ -553,11 +553,16 @@ def run_ours(args):
 # The file is stamped with the sha256 of the kernel sources it was captured from; a stale capture
 # (sources changed since) is reported as null instead of a number that no longer describes the code.
 # --------------------------------------------------------------------------------------------
+# the sources of the kernels the timed step launches (the traffic figures describe these)
+STEP_KERNEL_SOURCES = ("common.cuh", "prepare_common.cuh", "prepare.cu", "prepare_lsd.cu", "layout.cu",
+                       "pool_fwd_cells.cu", "pool_bwd.cu")
+
+
 def _kernel_sources_digest():
     import hashlib
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, "rcbevdet_b200", "csrc")
-    for name in sorted(os.listdir(csrc)):
+    for name in STEP_KERNEL_SOURCES:
         with open(os.path.join(csrc, name), "rb") as f:
             h.update(name.encode() + b"\0" + f.read())
     return h.hexdigest()[:16]

@@ -56,9 +56,12 @@ def test_gpu_arm_prints_one_json_line_with_roofline():
     assert set(d["stages_ms"]) == {"prepare", "feat_rows", "fwd", "og_rows", "bwd"}
     # the e2e step ships the calibration, not a materialised coor
     assert e2e["h2d_bytes_per_step"] < d["e2e_coor_input"]["h2d_bytes_per_step"] - 40e6
-    assert d["clocks"]["samples_pre_spin"] > 20
+    assert d["clocks"]["samples_pre_spin"] > 20, d["clocks"]
     cfg = d["configs"]
     assert "error" not in cfg, cfg
     for name in ("temporal_8f", "hires_256_B1", "hires_256_B8", "radar_128", "radar_512"):
-        assert cfg[name]["samples_per_s"] > 0, name
-    assert "prepare_torch_ms" in d["reference_gpu"]
+        assert cfg[name]["samples_per_s"] > 0, (name, cfg[name])
+    # the checker-side legs report their own failure instead of taking the line down
+    assert "prepare_torch_ms" in d["reference_gpu"] or "error" in d["reference_gpu"], d["reference_gpu"]
+    st = d["variants"]["strips"]
+    assert st["status"] == 0 and st["fwd_rel_err_vs_cells"] < 1e-5 and st["fwd_ms"] > 0 and st["bwd_ms"] > 0, st
