@@ -43,9 +43,16 @@ namespace rcb {
 constexpr int kStripV = 16;    // pixels per strip
 constexpr int kStripCols = 8;  // adjacent image columns per CTA: 32-byte runs of depth / point_cell = whole sectors
 constexpr int kGroupPix = kStripV * kStripCols;  // (pixel, column) pairs of a CTA per depth bin
-constexpr int kCombineCells = 64;
+#ifndef RCB_COMBINE_CELLS
+#define RCB_COMBINE_CELLS 64
+#endif
+constexpr int kCombineCells = RCB_COMBINE_CELLS;  // cells per CTA of the combine / spread kernels (64 per lane-group slot)
+constexpr int kSpreadCells = 64;
 constexpr int kIndexBlock = 256;  // cells per CTA of k_cellseg_index
 constexpr int kNoLabel = 0xffff;
+#ifndef RCB_COMBINE_CTAS
+#define RCB_COMBINE_CTAS 1  // minimum resident CTAs per SM the combine / spread kernels are compiled for
+#endif
 
 struct StripGeom {
   int n_img, D, H, W, HW;
@@ -652,41 +659,63 @@ struct CombineParams {
 // contiguous piece of it.  A (B, C, cells) store instruction writes four channel rows x eight
 // consecutive cells (whole 32-byte sectors).  No shared memory, no barrier, no indirection.
 template <int CPL>
-__global__ void __launch_bounds__(256) k_fwd_combine(CombineParams p) {
+__global__ void __launch_bounds__(256, RCB_COMBINE_CTAS) k_fwd_combine(CombineParams p) {
   pdl_prologue();
   if (*p.status != 0) return;
   constexpr int C = 16 * CPL;
+  constexpr int kPer = kCombineCells / 64;  // cells per lane group: their loads are in flight together
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x / p.tiles_per_sample, c0 = (blockIdx.x % p.tiles_per_sample) * kCombineCells;
-  const int cell = c0 + warp * 8 + (lane >> 2), sub = lane & 3;
-  if (cell >= p.cps) return;
-  const size_t gc = (size_t)b * p.cps + cell;
-  const int r0 = p.seg_start[gc], r1 = p.seg_start[gc + 1];
-  float4 acc[CPL];
+  const int sub = lane & 3;
+  int cell[kPer], r0[kPer], n[kPer];
 #pragma unroll
-  for (int q = 0; q < CPL; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 *src = reinterpret_cast<const float4 *>(p.rows + (size_t)r0 * C) + sub;
-  for (int r = r0; r < r1; ++r, src += C / 4) {
-    float4 v[CPL];
-#pragma unroll
-    for (int q = 0; q < CPL; ++q) v[q] = src[4 * q];
-#pragma unroll
-    for (int q = 0; q < CPL; ++q) acc[q].x += v[q].x, acc[q].y += v[q].y, acc[q].z += v[q].z, acc[q].w += v[q].w;
+  for (int u = 0; u < kPer; ++u) {
+    cell[u] = c0 + (warp * kPer + u) * 8 + (lane >> 2);
+    const bool ok = cell[u] < p.cps;
+    const size_t gc = (size_t)b * p.cps + (ok ? cell[u] : 0);
+    r0[u] = p.seg_start[gc];
+    n[u] = ok ? p.seg_start[gc + 1] - r0[u] : -1;
   }
-  if (p.layout == RCB_LAYOUT_B_C_CELLS) {
-    float *dst = p.out + (size_t)b * C * p.cps + cell;
+  float4 acc[kPer][CPL];
+  int nmax = 0;
 #pragma unroll
-    for (int q = 0; q < CPL; ++q) {
-      const size_t ch = (size_t)(sub + 4 * q) * 4;
-      st_stream_f32(dst + (ch + 0) * p.cps, acc[q].x);
-      st_stream_f32(dst + (ch + 1) * p.cps, acc[q].y);
-      st_stream_f32(dst + (ch + 2) * p.cps, acc[q].z);
-      st_stream_f32(dst + (ch + 3) * p.cps, acc[q].w);
+  for (int u = 0; u < kPer; ++u) {
+    nmax = max(nmax, n[u]);
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) acc[u][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int i = 0; i < nmax; ++i) {
+    float4 v[kPer][CPL];
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const float4 *src = reinterpret_cast<const float4 *>(p.rows + (size_t)(r0[u] + (i < n[u] ? i : 0)) * C) + sub;
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) v[u][q] = i < n[u] ? src[4 * q] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  } else {
-    float4 *dst = reinterpret_cast<float4 *>(p.out + gc * C) + sub;
 #pragma unroll
-    for (int q = 0; q < CPL; ++q) st_stream_f4(dst + 4 * q, acc[q]);
+    for (int u = 0; u < kPer; ++u)
+#pragma unroll
+      for (int q = 0; q < CPL; ++q)
+        acc[u][q].x += v[u][q].x, acc[u][q].y += v[u][q].y, acc[u][q].z += v[u][q].z, acc[u][q].w += v[u][q].w;
+  }
+#pragma unroll
+  for (int u = 0; u < kPer; ++u) {
+    if (n[u] < 0) continue;
+    if (p.layout == RCB_LAYOUT_B_C_CELLS) {
+      float *dst = p.out + (size_t)b * C * p.cps + cell[u];
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) {
+        const size_t ch = (size_t)(sub + 4 * q) * 4;
+        st_stream_f32(dst + (ch + 0) * p.cps, acc[u][q].x);
+        st_stream_f32(dst + (ch + 1) * p.cps, acc[u][q].y);
+        st_stream_f32(dst + (ch + 2) * p.cps, acc[u][q].z);
+        st_stream_f32(dst + (ch + 3) * p.cps, acc[u][q].w);
+      }
+    } else {
+      float4 *dst = reinterpret_cast<float4 *>(p.out + ((size_t)b * p.cps + cell[u]) * C) + sub;
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) st_stream_f4(dst + 4 * q, acc[u][q]);
+    }
   }
 }
 
@@ -695,12 +724,12 @@ __global__ void __launch_bounds__(256) k_fwd_combine(CombineParams p) {
 // ------------------------------------------------------------------------------------------------
 // the mirror image of k_fwd_combine: the out_grad row of a cell goes to each of the cell's segments
 template <int CPL>
-__global__ void __launch_bounds__(256) k_bwd_spread(CombineParams p) {
+__global__ void __launch_bounds__(256, RCB_COMBINE_CTAS) k_bwd_spread(CombineParams p) {
   pdl_prologue();
   if (*p.status != 0) return;
   constexpr int C = 16 * CPL;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x / p.tiles_per_sample, c0 = (blockIdx.x % p.tiles_per_sample) * kCombineCells;
+  const int b = blockIdx.x / p.tiles_per_sample, c0 = (blockIdx.x % p.tiles_per_sample) * kSpreadCells;
   const int cell = c0 + warp * 8 + (lane >> 2), sub = lane & 3;
   if (cell >= p.cps) return;
   const size_t gc = (size_t)b * p.cps + cell;
@@ -893,7 +922,7 @@ extern "C" int rcb_bev_pool_v2_bwd_strips(const rcb_pool_desc *d, const rcb_stri
   CombineParams c;
   c.status = pv.status, c.seg_start = pv.seg_start;
   c.rows = static_cast<float *>(rows), c.out = const_cast<float *>(out_grad);
-  c.cps = d->Z * d->Y * d->X, c.tiles_per_sample = ceil_div(c.cps, kCombineCells), c.layout = d->layout;
+  c.cps = d->Z * d->Y * d->X, c.tiles_per_sample = ceil_div(c.cps, kSpreadCells), c.layout = d->layout;
   rc = launch_combine(c, d->B, d->C, true, s);
   if (rc != RCB_OK) return rc;
   StripsParams p = strips_params(g, pv, depth, feat, static_cast<float *>(rows));
