@@ -48,6 +48,13 @@ constexpr int kGroupPix = kStripV * kStripCols;  // (pixel, column) pairs of a C
 #endif
 constexpr int kCombineCells = RCB_COMBINE_CELLS;  // cells per CTA of the combine / spread kernels (64 per lane-group slot)
 constexpr int kSpreadCells = 64;
+#ifndef RCB_WB_CHUNK
+#define RCB_WB_CHUNK 16
+#endif
+#ifndef RCB_STRIP_CTAS
+#define RCB_STRIP_CTAS 2
+#endif
+constexpr int kWChunk = RCB_WB_CHUNK;  // depth bins a W-build thread loads as one batch
 constexpr int kIndexBlock = 256;  // cells per CTA of k_cellseg_index
 constexpr int kNoLabel = 0xffff;
 #ifndef RCB_COMBINE_CTAS
@@ -433,17 +440,17 @@ __device__ __forceinline__ void strip_prologue(const StripsParams &p, float *s_W
       int cur = d_begin > 0 ? (int)lab[(size_t)(d_begin - 1) * kGroupPix] : kNoLabel;
       bool own = false;
       float acc = 0.f;
-      for (int d0 = d_begin; d0 < d_end; d0 += 32) {
-        int l[32];
-        float x[32];
+      for (int d0 = d_begin; d0 < d_end; d0 += kWChunk) {
+        int l[kWChunk];
+        float x[kWChunk];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < kWChunk; ++i) {
           const bool ok = d0 + i < d_end;
           l[i] = ok ? (int)lab[(size_t)(d0 + i) * kGroupPix] : -1;
           x[i] = ok ? ld_stream_f32(w + (size_t)(d0 + i) * g.HW) : 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < kWChunk; ++i) {
           if (l[i] < 0) break;
           if (l[i] != cur) {
             if (own && cur != kNoLabel) wrow[cur * kStripV] = acc;
@@ -487,7 +494,7 @@ __device__ __forceinline__ void load_strip_feat(const StripsParams &p, const Str
 }
 
 template <typename FeatT, int CPL>
-__global__ void __launch_bounds__(32 * kStripCols, CPL <= 5 ? 2 : 1) k_fwd_strips(StripsParams p) {
+__global__ void __launch_bounds__(32 * kStripCols, CPL <= 5 ? RCB_STRIP_CTAS : 1) k_fwd_strips(StripsParams p) {
   pdl_prologue();
   if (*p.status != 0) return;
   constexpr int C = 16 * CPL;
@@ -535,7 +542,7 @@ __global__ void __launch_bounds__(32 * kStripCols, CPL <= 5 ? 2 : 1) k_fwd_strip
 // j ends up with pixel (j >> 1) % 8), and overwrite the segment's W row once it has been consumed by
 // the feat_grad update.  At the end depth_grad[d][v] = W[label[d][v]][v], written coalesced.
 template <typename FeatT, int CPL>
-__global__ void __launch_bounds__(32 * kStripCols, 2) k_bwd_strips(StripsParams p) {
+__global__ void __launch_bounds__(32 * kStripCols, RCB_STRIP_CTAS) k_bwd_strips(StripsParams p) {
   pdl_prologue();
   if (*p.status != 0) return;
   constexpr int C = 16 * CPL;
