@@ -104,6 +104,30 @@ def test_auto_mode_switches_on_reuse():
     _close(second, oracle.to_bczyx(want), RTOL32, "strip kernels")
 
 
+def test_foreign_int64_ranks_take_the_strip_kernels_too():
+    """Ranks that did not come from this library's prepare (the oracle's, as int64 like the reference's
+    own): validated on the device once, then planned for the strip kernels like any other."""
+    import rcbevdet_b200 as rcb
+    from rcbevdet_b200 import rig, strips, plan as _plan
+    strips.set_mode("on")
+    grid = rig.R50_GRID
+    coor, depth, feat = _case(B=2, aug=6)
+    ranks, shape, feat_rows, want = _oracle_pool(coor, depth, feat, grid)
+    rb, rd, rf, st, ln = (torch.from_numpy(np.ascontiguousarray(r)).long().cuda() for r in ranks)
+    d = depth.cuda().requires_grad_(True)
+    f = feat.cuda().requires_grad_(True)
+    bev = rcb.bev_pool_v2(d, f.permute(0, 1, 3, 4, 2), rd, rf, rb, shape, st, ln)
+    plan = _plan.lookup(rd, rf, rb, st, ln, shape[0] * shape[1] * shape[2] * shape[3], depth.numel())
+    assert isinstance(plan.strips, strips.StripPlan)
+    _close(bev, oracle.to_bczyx(want), RTOL32, "bev")
+    og = torch.randn(bev.shape, generator=torch.Generator().manual_seed(9))
+    bev.backward(og.cuda())
+    og_rows = og.permute(0, 2, 3, 4, 1).contiguous().numpy()
+    want_dg, want_fg = oracle.bev_pool_v2_backward(og_rows, depth.numpy(), feat_rows, ranks[1], ranks[2], ranks[0], threads=8)
+    _close(d.grad, want_dg, RTOL32, "depth_grad")
+    _close(f.grad.permute(0, 1, 3, 4, 2), want_fg, RTOL32, "feat_grad")
+
+
 def test_non_frustum_ranks_fall_back():
     """Points scattered at random (no ray geometry): a strip meets more cells than the plan reserves,
     or a (cell, pixel) pair has several depth runs -> the plan refuses, the general kernels run."""
