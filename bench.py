@@ -363,6 +363,64 @@ def run_ours(args):
                         "backward = spread + strip pass, takes the (B,C,cells) gradient directly: no transpose); "
                         "compare fwd_f32_rows_ms and stages_ms.og_rows + stages_ms.bwd"}
 
+    def api_chain_variant(n=100):
+        """The whole step through the public chain API (rcb.voxel_pooling_v2 + autograd backward: what
+        LSSViewTransformer.voxel_pooling_v2 + loss.backward() run) with the default kernels (sorted
+        pipeline + cell-/pixel-stationary kernels) and with strips mode "chain" (no sort: frustum cells
+        -> strip plan -> strip kernels; the sorted pipeline enqueued behind them, gated on the device).
+        Eager and replayed from a CUDA graph (pure device time)."""
+        from rcbevdet_b200 import strips
+        coor, depth, feat, out_grad = sets[0]
+        og4 = out_grad.view(B, C, 128, 128)
+        res, outs = {}, {}
+        old = strips.MODE
+        try:
+            for mode in ("off", "chain"):
+                strips.set_mode(mode)
+
+                def one():
+                    d = depth.detach().requires_grad_(True)
+                    f = feat.detach().requires_grad_(True)
+                    bev = rcb.voxel_pooling_v2(coor, d, f, lo, iv, sz)
+                    bev.backward(og4)
+                    return bev.detach(), d.grad, f.grad
+
+                for _ in range(5):
+                    outs[mode] = one()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(n):
+                    one()
+                e1.record(stream)
+                torch.cuda.synchronize(dev)
+                res[f"{mode}_eager_ms"] = round(e0.elapsed_time(e1) / n, 5)
+                side = torch.cuda.Stream(dev)
+                with torch.cuda.stream(side):
+                    one()
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    one()
+                with torch.cuda.stream(side):
+                    for _ in range(5):
+                        graph.replay()
+                    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    g0.record(side)
+                    for _ in range(n):
+                        graph.replay()
+                    g1.record(side)
+                torch.cuda.synchronize(dev)
+                res[f"{mode}_graph_ms"] = round(g0.elapsed_time(g1) / n, 5)
+                del graph
+        finally:
+            strips.set_mode(old)
+        res["rel_err_chain_vs_default"] = [float((a - b).abs().max() / b.abs().max()) for a, b in zip(outs["chain"], outs["off"])]
+        res["samples_per_s_chain_graph"] = round(B / (res["chain_graph_ms"] * 1e-3), 1)
+        res["note"] = ("rcb.voxel_pooling_v2(coor, depth, feat) + backward on the device, same inputs every call "
+                       "(working set > L2); off = sorted pipeline + cell-/pixel-stationary kernels, chain = strips mode "
+                       "'chain' (no sort, no ranks materialised; fallback enqueued gated); *_graph_ms = CUDA-graph replay")
+        return res
+
     variants = None
     if not args.profile:
         # the opt-in channels-last result (no transposed write, gradient consumed in place): same step,
@@ -384,6 +442,7 @@ def run_ours(args):
                     "fwd_bf16_rows_ms": round(fwd_only(rows32.bfloat16(), _lib.DTYPE_BF16), 5),
                     "step_channels_last_ms": round(step_cl_ms, 5),
                     "strips": strips_variant(),
+                    "api_chain": api_chain_variant(),
                     "note": "fwd_*: forward kernel alone, same plan, 4 rotating outputs (inputs L2-warm); "
                             "step_channels_last_ms: the whole step with bev_pool_v2(..., channels_last=True) "
                             "semantics (rows written directly, channels-last out_grad used in place)"}

@@ -112,6 +112,23 @@ int rcb_voxel_pooling_prepare_from_calib(const rcb_prepare_desc *d, const rcb_fr
                                          int *cell_start, int *counts, void *workspace,
                                          size_t workspace_bytes, int device, rcb_stream_t stream);
 
+/* The first stage alone: point_cell[B*N*D*H*W] (BEV cell of every frustum point, -1 = outside the grid,
+ * view_transformer.py:230-249 per point), from `coor` (fr == NULL) or from the calibration (coor ==
+ * NULL).  It is all the strip plan (rcb_strip_plan_build) needs: a chain that never hands ranks to
+ * its caller -- LSSViewTransformer.voxel_pooling_v2, view_transformer.py:180-205 -- can pool without
+ * sorting at all (rcbevdet_b200/view_pool.py, strips mode "chain"). */
+int rcb_frustum_point_cells(const rcb_prepare_desc *d, const float *coor, const rcb_frustum_desc *fr,
+                            int *point_cell, int device, rcb_stream_t stream);
+
+/* Launch gate of the calling host thread (NULL clears it).  While it is set, the kernels behind
+ * rcb_voxel_pooling_prepare_v2 / _from_calib, rcb_bev_pool_v2_fwd (CSR path) and rcb_bev_pool_v2_bwd
+ * (structured path, its out_grad transpose included) are launched as usual but exit at once when
+ * *gate == 0 on the device; entry points that would take a kernel without a gate return
+ * RCB_ERR_UNSUPPORTED.  With gate = the status word of a strip plan this enqueues the general
+ * kernels as the fallback of the strip kernels (which exit when the word is non-zero) without
+ * reading the word back: exactly one of the two families does the work. */
+int rcb_set_launch_gate(const int *gate);
+
 /* Test hook (synchronous, allocates 16 bytes itself): the kernels replace the fp32 division of
  * view_transformer.py:231 by a reciprocal-based sequence that must round identically.  Sweeps all
  * 2^32 numerators for one divisor; *mismatches = quotients that differ from IEEE division in any
@@ -199,7 +216,8 @@ int rcb_bev_pool_v2_bwd(const rcb_pool_desc *d, const float *out_grad, const flo
  *         runs -- or has enqueued behind, gated on the same word -- the general entry points.
  *   rows: scratch of rcb_strip_rows_bytes() (one row of C floats per reserved segment; only the used
  *         rows are touched).
- *   cell_start (plan build only): the dense CSR of rcb_voxel_pooling_prepare_v2 / rcb_pool_build_cellmap.
+ *   cell_start (plan build only): unused since the plan builds its per-cell lists from its own counts
+ *         (may be NULL); the plan needs point_cell only -- see rcb_frustum_point_cells.
  * Supported: C in {64, 80, 128} forward, {64, 80} backward; D <= 256; B*Z*Y*X <= 2^24.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {

@@ -4,6 +4,7 @@ There is no fallback: if the CUDA library is missing every operator of this pack
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import os
 import threading
@@ -53,6 +54,8 @@ SIGNATURES = {
     "rcb_voxel_pooling_prepare_v2": (_i, [ctypes.POINTER(PrepareDesc)] + [_vp] * 9 + [_vp, _sz, _i, _vp]),
     "rcb_voxel_pooling_prepare_from_calib": (_i, [ctypes.POINTER(PrepareDesc), ctypes.POINTER(FrustumDesc)] +
                                              [_vp] * 8 + [_vp, _sz, _i, _vp]),
+    "rcb_frustum_point_cells": (_i, [ctypes.POINTER(PrepareDesc), _vp, ctypes.POINTER(FrustumDesc), _vp, _i, _vp]),
+    "rcb_set_launch_gate": (_i, [_vp]),
     "rcb_debug_exactdiv_sweep": (_i, [ctypes.c_float, ctypes.POINTER(ctypes.c_ulonglong),
                                       ctypes.POINTER(ctypes.c_ulonglong), _i]),
     "rcb_pool_validate_workspace_bytes": (_sz, [ctypes.POINTER(PoolDesc)]),
@@ -114,3 +117,18 @@ def ptr(t):
 def stream_ptr(device):
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+@contextlib.contextmanager
+def launch_gate(word):
+    """Inside the block the general entry points (prepare, cell-stationary forward, pixel-stationary
+    backward) launch kernels that exit at once when the device int32 `word[0]` is zero
+    (rcb_set_launch_gate); None = no gate."""
+    if word is None:
+        yield
+        return
+    lib().rcb_set_launch_gate(ptr(word))
+    try:
+        yield
+    finally:
+        lib().rcb_set_launch_gate(None)

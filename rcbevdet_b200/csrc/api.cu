@@ -23,7 +23,15 @@ int sm_count_cached(int device) {
   return cache[dev];
 }
 
+static thread_local const int *t_launch_gate = nullptr;
+const int *launch_gate() { return t_launch_gate; }
+
 }  // namespace rcb
+
+extern "C" int rcb_set_launch_gate(const int *gate) {
+  rcb::t_launch_gate = gate;
+  return RCB_OK;
+}
 
 extern "C" int rcb_version(void) { return 100; }
 

@@ -43,6 +43,14 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Launch gate (rcb_set_launch_gate, api.cu): while the calling host thread has a gate set, the kernels
+// of the general entry points (prepare, cell-stationary forward, pixel-stationary backward and its
+// out_grad transpose) are launched as usual but exit at once when *gate == 0.  It is how a chain
+// enqueues its fallback behind the strip kernels without reading their plan's status word back: the
+// gate IS that status word (0 = the strip kernels ran, non-zero = they refused and exited).
+const int *launch_gate();
+__device__ __forceinline__ bool gate_closed(const int *gate) { return gate != nullptr && *gate == 0; }
+
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 

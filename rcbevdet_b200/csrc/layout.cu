@@ -23,8 +23,9 @@ __device__ __forceinline__ unsigned short convert_elem<float, unsigned short>(fl
 
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256) k_planes_to_rows(const TIn *__restrict__ src, TOut *__restrict__ dst,
-                                                        int C, int HW, long long src_img_stride) {
+                                                        int C, int HW, long long src_img_stride, const int *gate) {
   pdl_prologue();
+  if (gate_closed(gate)) return;
   __shared__ TOut tile[32][33];
   const int img = blockIdx.z;
   const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -54,8 +55,9 @@ constexpr int kV4Pixels = 64;
 #define RCB_V4_MIN_HW 256
 #endif
 __global__ void __launch_bounds__(256) k_planes_to_rows_v4(const float *__restrict__ src, float *__restrict__ dst,
-                                                           int C, int HW, long long src_img_stride) {
+                                                           int C, int HW, long long src_img_stride, const int *gate) {
   pdl_prologue();
+  if (gate_closed(gate)) return;
   extern __shared__ float tile_v4[];  // [kV4Pixels][C + 1]
   const int P = C + 1;
   const int img = blockIdx.y;
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(256) k_planes_to_rows_v4(const float *__restri
 }
 
 int planes_to_rows_launch(const void *src, void *dst, int n_img, int C, int HW,
-                          long long src_img_stride, int elem_bytes, cudaStream_t s) {
+                          long long src_img_stride, int elem_bytes, cudaStream_t s, const int *gate) {
   if (n_img <= 0 || C <= 0 || HW <= 0) return RCB_OK;
   if (n_img > 65535) return RCB_ERR_UNSUPPORTED;
   if (elem_bytes == 4 && (C % 4) == 0 && (HW % 4) == 0 && HW >= RCB_V4_MIN_HW && C <= 256 && (src_img_stride % 4) == 0 &&
@@ -107,18 +109,18 @@ int planes_to_rows_launch(const void *src, void *dst, int n_img, int C, int HW,
     if (smem > 48 * 1024)
       RCB_CUDA_TRY(cudaFuncSetAttribute(k_planes_to_rows_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 g4(ceil_div(HW, kV4Pixels), n_img);
-    RCB_CUDA_TRY(launch_pdl(k_planes_to_rows_v4, g4, 256, smem, s, (const float *)src, (float *)dst, C, HW, src_img_stride));
+    RCB_CUDA_TRY(launch_pdl(k_planes_to_rows_v4, g4, 256, smem, s, (const float *)src, (float *)dst, C, HW, src_img_stride, gate));
     return RCB_OK;
   }
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), n_img);
   if (elem_bytes == 4)
-    RCB_CUDA_TRY(launch_pdl(k_planes_to_rows<float, float>, grid, 256, 0, s, (const float *)src, (float *)dst, C, HW, src_img_stride));
+    RCB_CUDA_TRY(launch_pdl(k_planes_to_rows<float, float>, grid, 256, 0, s, (const float *)src, (float *)dst, C, HW, src_img_stride, gate));
   else if (elem_bytes == 2)
     k_planes_to_rows<unsigned short, unsigned short>
-        <<<grid, 256, 0, s>>>((const unsigned short *)src, (unsigned short *)dst, C, HW, src_img_stride);
+        <<<grid, 256, 0, s>>>((const unsigned short *)src, (unsigned short *)dst, C, HW, src_img_stride, gate);
   else if (elem_bytes == -2)  // fp32 in, bf16 out
     k_planes_to_rows<float, unsigned short>
-        <<<grid, 256, 0, s>>>((const float *)src, (unsigned short *)dst, C, HW, src_img_stride);
+        <<<grid, 256, 0, s>>>((const float *)src, (unsigned short *)dst, C, HW, src_img_stride, gate);
   else
     return RCB_ERR_ARG;
   RCB_LAUNCH_CHECK();
@@ -136,5 +138,5 @@ extern "C" int rcb_planes_to_rows(const void *src, void *dst, int n_img, int C, 
   if (n_img < 0 || C < 0 || HW < 0) return RCB_ERR_ARG;
   DeviceGuard guard(device);
   if (guard.err) return guard.err;
-  return planes_to_rows_launch(src, dst, n_img, C, HW, src_img_stride, elem_bytes, (cudaStream_t)stream);
+  return planes_to_rows_launch(src, dst, n_img, C, HW, src_img_stride, elem_bytes, (cudaStream_t)stream, nullptr);
 }

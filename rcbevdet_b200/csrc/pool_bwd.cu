@@ -75,11 +75,13 @@ struct BwdPixelParams {
   float *feat_grad;
   int n_pixels, D, HW, DHW, C4;
   int H, W;  // 0 when unknown (then pixels are walked in memory order)
+  const int *gate;  // launch gate (common.cuh)
 };
 
 // kQ = 128-bit quads per lane (C <= 128*kQ)
 template <typename FeatT, int kQ>
 __global__ void __launch_bounds__(256) k_pool_bwd_pixels(BwdPixelParams p) {
+  if (gate_closed(p.gate)) return;
   const int lane = lane_id();
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const FeatT *feat = static_cast<const FeatT *>(p.feat);
@@ -202,6 +204,7 @@ __host__ __device__ inline size_t bwd16_smem_bytes(int d_chunk) {
 template <typename FeatT, int kNQ, int kNS>
 __global__ void __launch_bounds__(256, 4) k_pool_bwd_pixels16(BwdPixelParams p, int d_chunk) {
   pdl_prologue();
+  if (gate_closed(p.gate)) return;
   constexpr int kC = 64 * kNQ + 16 * kNS;
   extern __shared__ __align__(16) unsigned char bwd_smem[];
   int *s_cell = reinterpret_cast<int *>(bwd_smem);            // [d_chunk][17]
@@ -414,7 +417,7 @@ __global__ void __launch_bounds__(256)
 }
 
 int planes_to_rows_launch(const void *src, void *dst, int n_img, int C, int HW,
-                          long long src_img_stride, int elem_bytes, cudaStream_t s);
+                          long long src_img_stride, int elem_bytes, cudaStream_t s, const int *gate);
 
 template <typename FeatT>
 static int launch_pixels(BwdPixelParams &p, int sms, cudaStream_t s) {
@@ -467,7 +470,7 @@ extern "C" int rcb_bev_pool_v2_bwd(const rcb_pool_desc *d, const float *out_grad
   if (d->layout == RCB_LAYOUT_B_C_CELLS) {
     const size_t need = (size_t)d->B * cps * d->C * 4;
     if (!workspace || workspace_bytes < need) return RCB_ERR_WORKSPACE;
-    rc = planes_to_rows_launch(out_grad, workspace, d->B, d->C, cps, (long long)d->C * cps, 4, s);
+    rc = planes_to_rows_launch(out_grad, workspace, d->B, d->C, cps, (long long)d->C * cps, 4, s, launch_gate());
     if (rc != RCB_OK) return rc;
     og_rows = static_cast<const float *>(workspace);
   }
@@ -486,12 +489,14 @@ extern "C" int rcb_bev_pool_v2_bwd(const rcb_pool_desc *d, const float *out_grad
     p.n_pixels = d->n_pixels, p.D = d->D, p.HW = d->HW, p.DHW = d->D * d->HW, p.C4 = d->C / 4;
     p.H = d->H > 0 && d->HW % d->H == 0 ? d->H : 1;
     p.W = d->HW / p.H;
+    p.gate = launch_gate();
     switch (d->feat_dtype) {
       case RCB_DTYPE_F32: return launch_pixels<float>(p, sms, s);
       case RCB_DTYPE_BF16: return launch_pixels<__nv_bfloat16>(p, sms, s);
       default: return launch_pixels<__half>(p, sms, s);
     }
   }
+  if (launch_gate()) return RCB_ERR_UNSUPPORTED;  // the point kernel takes no launch gate
   // general path (bev_pool.py:67-68 zero-fill, then accumulate)
   RCB_CUDA_TRY(cudaMemsetAsync(depth_grad, 0, (size_t)d->n_depth * 4, s));
   RCB_CUDA_TRY(cudaMemsetAsync(feat_grad, 0, (size_t)d->n_pixels * d->C * 4, s));

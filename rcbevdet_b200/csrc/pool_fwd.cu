@@ -111,6 +111,7 @@ extern "C" int rcb_bev_pool_v2_fwd(const rcb_pool_desc *d, const float *depth, c
   // A CSR without interval arrays is the sync-free fused chain (n_points is only an upper bound
   // there): it cannot fall back to the interval kernel, so say so instead of returning zeros.
   if (cell_start != nullptr && d->n_points > 0 && (!interval_lengths || !interval_starts)) return RCB_ERR_UNSUPPORTED;
+  if (launch_gate()) return RCB_ERR_UNSUPPORTED;  // the interval kernel takes no launch gate
   // general path: zero-fill (bev_pool.py:27) then one warp per interval
   RCB_CUDA_TRY(cudaMemsetAsync(out, 0, out_bytes, s));
   if (d->n_intervals == 0) return RCB_OK;

@@ -70,6 +70,7 @@ struct FwdCellsParams {
   int B;
   unsigned row_bytes;
   FastDiv by_B, by_tiles_x;
+  const int *gate;  // launch gate (common.cuh)
 };
 
 // i-th element of {c, c-1, c+1, c-2, c+2, ...} clipped to [0, n), c = n / 2
@@ -104,6 +105,7 @@ struct FwdChunk {
 template <typename FeatT, int kLanes, int kQ>
 __global__ void __launch_bounds__(32 * kFwdWarps, RCB_FWD_CTAS) k_fwd_cells(FwdCellsParams p) {
   pdl_prologue();
+  if (gate_closed(p.gate)) return;
   extern __shared__ __align__(16) float cells_ts[];  // [C][kTilePitch] write-out tile (B_C_CELLS layout only)
   __shared__ __align__(16) uint2 s_ent[kFwdWarps][32];
   __shared__ int s_lo[kPatchCells], s_hi[kPatchCells];
@@ -405,6 +407,7 @@ int fwd_cells_launch(const rcb_pool_desc *d, const float *depth, const void *fea
   p.tiles_x = ceil_div(p.X, kPatchX), p.tiles_r = ceil_div(p.R, kPatchY);
   p.cells_per_sample = d->Z * d->Y * d->X, p.layout = d->layout, p.B = d->B;
   p.row_bytes = (unsigned)d->C * elem;
+  p.gate = launch_gate();
   p.by_B = FastDiv::make((unsigned)p.B), p.by_tiles_x = FastDiv::make((unsigned)p.tiles_x);
   const long long grid = (long long)d->B * p.tiles_r * p.tiles_x;
   switch (d->feat_dtype) {

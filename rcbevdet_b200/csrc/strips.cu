@@ -19,7 +19,7 @@
 // (every depth bin of a pixel in the segment gets the pixel's dot product as depth_grad) and one
 // rank-1 update W[s] x row of the strip's feat_grad registers.
 //
-//   plan (once per set of ranks; k_strip_plan + k_cellseg_index)
+//   plan (from point_cell alone; k_strip_plan + k_seg_prefix / k_seg_fill / k_seg_assign)
 //       per point : LABEL = index of its segment inside its strip (0xffff: dropped)
 //       per segment: the ROW it owns in a workspace
 //       per cell  : seg_start[c] .. seg_start[c+1]: the cell's segments own consecutive rows, in
@@ -55,7 +55,7 @@ constexpr int kSpreadCells = 64;
 #define RCB_STRIP_CTAS 2
 #endif
 constexpr int kWChunk = RCB_WB_CHUNK;  // depth bins a W-build thread loads as one batch
-constexpr int kIndexBlock = 256;  // cells per CTA of k_cellseg_index
+constexpr int kIndexBlock = 256;  // cells per CTA of k_seg_prefix / k_seg_assign
 constexpr int kNoLabel = 0xffff;
 #ifndef RCB_COMBINE_CTAS
 #define RCB_COMBINE_CTAS 1  // minimum resident CTAs per SM the combine / spread kernels are compiled for
@@ -134,11 +134,12 @@ __device__ __forceinline__ void strip_block(const StripGeom &g, int bid, int &im
 // plan
 // ------------------------------------------------------------------------------------------------
 struct StripPlanParams {
-  const int *point_cell, *cell_start;
+  const int *point_cell;
   int *status;
   int *nseg;
   unsigned short *label;
-  int *cell_nseg, *block_sum, *raw;
+  int *cell_nseg, *block_sum;
+  int *seg_dst;  // plan kernel: the segment's CELL (k_seg_assign replaces it by the segment's row)
   StripGeom g;
   int vec4;
 };
@@ -244,8 +245,8 @@ __global__ void __launch_bounds__(32 * kStripCols) k_strip_plan(StripPlanParams 
         for (unsigned m = (unsigned)(cur & 0xffffu); m; m &= m - 1) row[__ffs(m) - 1] = j;
       }
       if (first && j < g.seg_cap) {
-        const int k = atomicAdd(&p.cell_nseg[cell], 1);
-        p.raw[p.cell_start[cell] + k] = strip * g.seg_cap + j;
+        p.seg_dst[(size_t)strip * g.seg_cap + j] = cell;
+        atomicAdd(&p.cell_nseg[cell], 1);
         atomicAdd(&p.block_sum[cell / kIndexBlock], 1);
       }
       segs += __popc(fm);
@@ -302,23 +303,23 @@ __device__ __forceinline__ void cswap(int &a, int &b) {
   a = lo, b = hi;
 }
 
-// Per cell: seg_start (exclusive prefix of the segment counts: block totals were counted by the plan
-// kernel, so a CTA only sums the totals of the blocks before it) and, for every segment of the cell,
-// the workspace row it owns: seg_start[c] + its rank in ascending (strip, segment) order -- the
-// claimed order of the atomics never reaches an output.  Lists of <= 8 (all but a few hundred cells
-// next to the cameras) are sorted by their own thread in registers, longer ones by the warp.
-__global__ void __launch_bounds__(kIndexBlock) k_cellseg_index(const int *cell_nseg, const int *block_sum,
-                                                               const int *cell_start, const int *raw, int *seg_start,
-                                                               int *seg_dst, int n_cells, int *status) {
+// The per-cell segment lists need no input besides the plan kernel's own counts (in particular not the
+// sorted ranks' CSR: the plan is built from point_cell alone, so a chain that never exposes ranks can
+// skip the sort altogether -- rcb_voxel_pooling chain in view_pool.py):
+//   k_seg_prefix : seg_start = exclusive prefix of the per-cell segment counts (block totals were
+//                  counted by the plan kernel, so a CTA only sums the totals of the blocks before it)
+//   k_seg_fill   : every segment claims a slot of its cell's list (integer countdown of the cell's count)
+//   k_seg_assign : the cell's list sorted ascending by (strip, segment); the segment at rank r owns the
+//                  workspace row seg_start[c] + r -- the claimed order of the atomics never reaches an
+//                  output.  Lists of <= 8 (all but a few hundred cells next to the cameras) are sorted
+//                  by their own thread in registers, longer ones by the warp.
+__global__ void __launch_bounds__(kIndexBlock) k_seg_prefix(const int *cell_nseg, const int *block_sum, int *seg_start,
+                                                            int n_cells) {
   pdl_prologue();
   __shared__ int s_part[kIndexBlock / 32], s_wsum[kIndexBlock / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = blockIdx.x * kIndexBlock + tid;
-  int cnt = 0, cs = 0;
-  if (c < n_cells) {
-    cnt = cell_nseg[c];
-    if (cnt) cs = cell_start[c];
-  }
+  const int cnt = c < n_cells ? cell_nseg[c] : 0;
   int part = 0;
   for (int i = tid; i < (int)blockIdx.x; i += kIndexBlock) part += block_sum[i];
   int incl = cnt;
@@ -336,7 +337,35 @@ __global__ void __launch_bounds__(kIndexBlock) k_cellseg_index(const int *cell_n
   for (int w = 0; w < kIndexBlock / 32; ++w) start += s_part[w] + (w < warp ? s_wsum[w] : 0);
   if (c < n_cells) seg_start[c] = start;
   if (c == n_cells - 1) seg_start[n_cells] = start + cnt;
+}
 
+constexpr int kFillThreads = 128;
+
+// one CTA per strip
+__global__ void __launch_bounds__(kFillThreads) k_seg_fill(const int *nseg, const int *seg_dst, const int *seg_start,
+                                                           int *cell_nseg, int *raw, int seg_cap) {
+  pdl_prologue();
+  const int strip = blockIdx.x;
+  const int n = min(nseg[strip], seg_cap);
+  for (int j = threadIdx.x; j < n; j += kFillThreads) {
+    const int id = strip * seg_cap + j;
+    const int cell = seg_dst[id];
+    const int k = atomicSub(&cell_nseg[cell], 1) - 1;
+    raw[seg_start[cell] + k] = id;
+  }
+}
+
+__global__ void __launch_bounds__(kIndexBlock) k_seg_assign(const int *seg_start, const int *raw, int *seg_dst,
+                                                            int n_cells, int *status) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * kIndexBlock + threadIdx.x;
+  int cnt = 0, cs = 0;
+  if (c < n_cells) {
+    cs = seg_start[c];
+    cnt = seg_start[c + 1] - cs;
+  }
+  const int start = cs;
   if (cnt >= 1 && cnt <= 8) {
     int v[8];
 #pragma unroll
@@ -858,7 +887,8 @@ extern "C" int rcb_strip_plan_build(const rcb_strip_desc *d, const int *point_ce
                                     void *plan, size_t plan_bytes, int device, rcb_stream_t stream) {
   StripGeom g;
   if (!make_geom(d, &g)) return RCB_ERR_UNSUPPORTED;
-  if (!point_cell || !cell_start || !plan) return RCB_ERR_ARG;
+  (void)cell_start;  // kept in the signature for callers of the first revision; the plan no longer reads it
+  if (!point_cell || !plan) return RCB_ERR_ARG;
   PlanView pv = plan_view(g, plan);
   if (plan_bytes < pv.bytes) return RCB_ERR_WORKSPACE;
   if (((uintptr_t)plan % 16) != 0) return RCB_ERR_ALIGN;
@@ -867,17 +897,20 @@ extern "C" int rcb_strip_plan_build(const rcb_strip_desc *d, const int *point_ce
   cudaStream_t s = (cudaStream_t)stream;
   RCB_CUDA_TRY(cudaMemsetAsync(plan, 0, pv.zero_bytes, s));  // status, segment counts per cell and per block
   StripPlanParams p;
-  p.point_cell = point_cell, p.cell_start = cell_start, p.status = pv.status, p.nseg = pv.nseg, p.label = pv.label;
-  p.cell_nseg = pv.cell_nseg, p.block_sum = pv.block_sum, p.raw = pv.raw, p.g = g;
+  p.point_cell = point_cell, p.status = pv.status, p.nseg = pv.nseg, p.label = pv.label;
+  p.cell_nseg = pv.cell_nseg, p.block_sum = pv.block_sum, p.seg_dst = pv.seg_dst, p.g = g;
   p.vec4 = (g.W % 4) == 0 && (((uintptr_t)point_cell) % 16) == 0;
   const size_t smem = (size_t)kStripCols * g.D * kStripV * 4 + (size_t)kStripCols * g.ent_cap * 8;
   int rc = set_smem(k_strip_plan, smem);
   if (rc != RCB_OK) return rc;
-  k_strip_plan<<<(unsigned)g.n_groups, 32 * kStripCols, smem, s>>>(p);
-  RCB_LAUNCH_CHECK();
-  RCB_CUDA_TRY(launch_pdl(k_cellseg_index, (unsigned)ceil_div(g.n_cells, kIndexBlock), kIndexBlock, 0, s,
-                          (const int *)pv.cell_nseg, (const int *)pv.block_sum, cell_start, (const int *)pv.raw,
-                          pv.seg_start, pv.seg_dst, g.n_cells, pv.status));
+  RCB_CUDA_TRY(launch_pdl(k_strip_plan, (unsigned)g.n_groups, 32 * kStripCols, smem, s, p));
+  const unsigned index_blocks = (unsigned)ceil_div(g.n_cells, kIndexBlock);
+  RCB_CUDA_TRY(launch_pdl(k_seg_prefix, index_blocks, kIndexBlock, 0, s, (const int *)pv.cell_nseg,
+                          (const int *)pv.block_sum, pv.seg_start, g.n_cells));
+  RCB_CUDA_TRY(launch_pdl(k_seg_fill, (unsigned)g.n_strips, kFillThreads, 0, s, (const int *)pv.nseg,
+                          (const int *)pv.seg_dst, (const int *)pv.seg_start, pv.cell_nseg, pv.raw, g.seg_cap));
+  RCB_CUDA_TRY(launch_pdl(k_seg_assign, index_blocks, kIndexBlock, 0, s, (const int *)pv.seg_start,
+                          (const int *)pv.raw, pv.seg_dst, g.n_cells, pv.status));
   return RCB_OK;
 }
 

@@ -81,7 +81,7 @@ def pack_calib(sensor2ego, ego2global, cam2imgs, post_rots, post_trans, bda):
     return cam.contiguous(), bda.reshape(B, 9).float().contiguous()
 
 
-def _launch(desc, dev, coor=None, frustum=None):
+def _launch(desc, dev, coor=None, frustum=None, point_cell=None):
     lib = _lib.lib()
     P = desc.B * desc.N * desc.D * desc.H * desc.W
     gx, gy, gz = (int(desc.size[k]) for k in range(3))
@@ -98,7 +98,7 @@ def _launch(desc, dev, coor=None, frustum=None):
     n_iv = max(1, min(P, n_cells))
     r.interval_starts = torch.empty(n_iv, **i32)
     r.interval_lengths = torch.empty(n_iv, **i32)
-    r.point_cell = torch.empty(P + 4, **i32)
+    r.point_cell = torch.empty(P + 4, **i32) if point_cell is None else point_cell
     r.cell_start = torch.empty(n_cells + 1, **i32)
     r.counts = torch.empty(4, **i32)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -118,22 +118,15 @@ def _launch(desc, dev, coor=None, frustum=None):
     return r
 
 
-def prepare_async(coor, grid_lower_bound, grid_interval, grid_size):
-    """Launch the pipeline; nothing is read back.  Outputs have capacity P (ranks) and
-    min(P, cells) (intervals); `counts` (device int32[4]) holds {n_kept, n_intervals}."""
+def _coor_args(coor, grid_lower_bound, grid_interval, grid_size):
     desc = _desc(coor, grid_lower_bound, grid_interval, grid_size)
     coor = coor.detach()
     if coor.dtype != torch.float32:
         coor = coor.float()
-    coor = coor.contiguous()
-    return _launch(desc, coor.device, coor=coor)
+    return desc, coor.contiguous()
 
 
-def prepare_from_calib_async(calib, axes, grid_lower_bound, grid_interval, grid_size, device=None):
-    """SURVEY.md 8(f-1): get_lidar_coor fused into prepare.  `calib` = the six tensors of
-    get_lidar_coor's signature (or an already packed (cam, bda) pair from pack_calib), `axes` =
-    frustum_axes(...).  Host tensors are packed on the host and only ~5 KB are uploaded; `coor`
-    (12 bytes per frustum point) is never materialised."""
+def _calib_args(calib, axes, grid_lower_bound, grid_interval, grid_size, device):
     cam, bda = pack_calib(*calib) if len(calib) == 6 else calib
     if device is None:
         device = cam.device if cam.is_cuda else torch.device("cuda", torch.cuda.current_device())
@@ -150,8 +143,62 @@ def prepare_from_calib_async(calib, axes, grid_lower_bound, grid_interval, grid_
     desc.lower[:] = _grid3(grid_lower_bound, "grid_lower_bound")
     desc.interval[:] = _grid3(grid_interval, "grid_interval")
     desc.size[:] = _grid3(grid_size, "grid_size")
-    r = _launch(desc, device, frustum=(u, v, d, cam, bda))
+    return desc, device, (u, v, d, cam, bda)
+
+
+class FrustumCells:
+    """The first prepare stage alone (rcb_frustum_point_cells): point_cell, and what is needed to run
+    the rest of the pipeline on the same input later (`launch_rest`)."""
+
+    __slots__ = ("desc", "device", "coor", "frustum", "point_cell", "grid", "B", "D", "H", "W", "HW", "P",
+                 "n_img", "n_cells")
+
+    def launch_rest(self):
+        """The full pipeline on the same input (point_cell is rewritten with the same values)."""
+        return _launch(self.desc, self.device, coor=self.coor, frustum=self.frustum, point_cell=self.point_cell)
+
+
+def point_cells_async(coor=None, calib=None, axes=None, grid_lower_bound=None, grid_interval=None, grid_size=None,
+                      device=None):
+    """BEV cell of every frustum point (-1 = outside), from `coor` or from the calibration; no sort,
+    no read-back."""
+    r = FrustumCells()
+    if coor is not None:
+        r.desc, r.coor = _coor_args(coor, grid_lower_bound, grid_interval, grid_size)
+        r.device, r.frustum = r.coor.device, None
+    else:
+        r.desc, r.device, r.frustum = _calib_args(calib, axes, grid_lower_bound, grid_interval, grid_size, device)
+        r.coor = None
+    d = r.desc
+    gx, gy, gz = (int(d.size[k]) for k in range(3))
+    r.grid = (gz, gy, gx)
+    r.B, r.D, r.H, r.W, r.HW, r.n_img = d.B, d.D, d.H, d.W, d.H * d.W, d.B * d.N
+    r.P, r.n_cells = d.B * d.N * d.D * d.H * d.W, d.B * gx * gy * gz
+    r.point_cell = torch.empty(r.P + 4, dtype=torch.int32, device=r.device)
+    fd = None
+    if r.frustum is not None:
+        fd = _lib.FrustumDesc()
+        fd.u, fd.v, fd.d, fd.cam, fd.bda = (t.data_ptr() for t in r.frustum)
+    _lib.check(_lib.lib().rcb_frustum_point_cells(ctypes.byref(d), _lib.ptr(r.coor), ctypes.byref(fd) if fd is not None else None,
+                                                  _lib.ptr(r.point_cell), r.device.index, _lib.stream_ptr(r.device)),
+               "rcb_frustum_point_cells")
     return r
+
+
+def prepare_async(coor, grid_lower_bound, grid_interval, grid_size):
+    """Launch the pipeline; nothing is read back.  Outputs have capacity P (ranks) and
+    min(P, cells) (intervals); `counts` (device int32[4]) holds {n_kept, n_intervals}."""
+    desc, coor = _coor_args(coor, grid_lower_bound, grid_interval, grid_size)
+    return _launch(desc, coor.device, coor=coor)
+
+
+def prepare_from_calib_async(calib, axes, grid_lower_bound, grid_interval, grid_size, device=None):
+    """SURVEY.md 8(f-1): get_lidar_coor fused into prepare.  `calib` = the six tensors of
+    get_lidar_coor's signature (or an already packed (cam, bda) pair from pack_calib), `axes` =
+    frustum_axes(...).  Host tensors are packed on the host and only ~5 KB are uploaded; `coor`
+    (12 bytes per frustum point) is never materialised."""
+    desc, device, frustum = _calib_args(calib, axes, grid_lower_bound, grid_interval, grid_size, device)
+    return _launch(desc, device, frustum=frustum)
 
 
 def _finish(r):

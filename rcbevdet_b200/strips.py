@@ -28,14 +28,19 @@ BWD_CHANNELS = (64, 80)
 #           reference, each bit-reproducible): with "auto" the first and the second call on the same
 #           inputs differ in the last bits, which is why it is not the default.
 #   "on"  : strip kernels for forward and backward, plan built at first use
-# Environment: RCB_STRIPS=off|auto|on.
+#   "chain": bev_pool_v2 as "off"; voxel_pooling_v2 / voxel_pooling_v2_from_calib / lss_view_transform --
+#           the chains that never hand ranks to their caller -- pool WITHOUT SORTING: frustum cells ->
+#           strip plan (it needs point_cell only) -> strip kernels, and behind them, gated on the
+#           plan's status word on the device, the sorted pipeline + cell-/pixel-stationary kernels as
+#           the fallback (no read-back: exactly one family does the work).  view_pool.py.
+# Environment: RCB_STRIPS=off|auto|on|chain.
 MODE = os.environ.get("RCB_STRIPS", "off").lower()
 
 
 def set_mode(mode):
     global MODE
-    if mode not in ("auto", "on", "off"):
-        raise ValueError("mode must be 'auto', 'on' or 'off'")
+    if mode not in ("auto", "on", "off", "chain"):
+        raise ValueError("mode must be 'auto', 'on', 'off' or 'chain'")
     MODE = mode
 
 
@@ -82,6 +87,7 @@ def build(point_cell, cell_start, n_img, D, H, W, n_cells):
         return None
     dev = point_cell.device
     buf = torch.empty(n, dtype=torch.uint8, device=dev)
+    # cell_start is no longer read by the plan (it builds its per-cell lists from its own counts)
     _lib.check(lib.rcb_strip_plan_build(ctypes.byref(d), _lib.ptr(point_cell), _lib.ptr(cell_start), _lib.ptr(buf),
                                         n, dev.index, _lib.stream_ptr(dev)), "rcb_strip_plan_build")
     return StripPlan(d, buf, cell_start)
@@ -121,7 +127,7 @@ def _for_plan(plan, desc):
 
 
 def for_forward(plan, desc):
-    if MODE == "off" or desc.C not in FWD_CHANNELS:
+    if MODE in ("off", "chain") or desc.C not in FWD_CHANNELS:
         return None
     plan.uses += 1
     if MODE == "auto" and plan.uses < 2 and plan.strips is None:

@@ -14,7 +14,7 @@ import ctypes
 import torch
 
 from . import _lib, bev_pool as _bp, plan as _plan, strips as _strips
-from .prepare import prepare_async, prepare_from_calib_async
+from .prepare import point_cells_async, prepare_async, prepare_from_calib_async
 
 
 class _ViewPool(torch.autograd.Function):
@@ -56,6 +56,93 @@ class _ViewPool(torch.autograd.Function):
         return depth_grad, feat_grad, None, None
 
 
+def _chain_desc(cells, depth_c, rows, channels_last):
+    gz, gy, gx = cells.grid
+    d = _lib.PoolDesc()
+    d.n_points, d.n_intervals, d.C = cells.P, 0, rows.shape[1]
+    d.B, d.Z, d.Y, d.X = cells.B, gz, gy, gx
+    d.n_depth, d.n_pixels = depth_c.numel(), rows.shape[0]
+    d.D, d.HW, d.H = cells.D, cells.HW, cells.H
+    d.layout = _lib.LAYOUT_CELLS_C if channels_last else _lib.LAYOUT_B_C_CELLS
+    d.feat_dtype, d.flags = _bp._DTYPES[rows.dtype], _lib.PLAN_ALL
+    if d.n_depth != cells.P or d.n_pixels * d.D != d.n_depth:
+        raise ValueError("depth / feat shapes do not match the frustum that `coor` describes")
+    return d
+
+
+class _ChainPool(torch.autograd.Function):
+    """The sort-free chain (strips mode "chain"): strip kernels on a plan built from point_cell alone;
+    behind them, gated on the plan's status word, the sorted pipeline + cell-/pixel-stationary kernels.
+    Nothing is read back; the kernels of the family that does not apply exit at once."""
+
+    @staticmethod
+    def forward(ctx, depth, feat, cells, sp, channels_last=False):
+        dev = depth.device
+        depth_c = depth.detach().contiguous().float()
+        rows = _bp.feat_rows(feat.detach())
+        d = _chain_desc(cells, depth_c, rows, channels_last)
+        gz, gy, gx = cells.grid
+        shape = (cells.B, gz, gy, gx, d.C) if channels_last else (cells.B, d.C, gz, gy, gx)
+        out = torch.empty(shape, dtype=torch.float32, device=dev)
+        _strips.forward(sp, d, depth_c, rows, out)
+        with _lib.launch_gate(sp.status_tensor()):
+            prepared = cells.launch_rest()
+            _bp.pool_forward(d, depth_c, rows, prepared.ranks_depth, prepared.ranks_feat, prepared.ranks_bev, None,
+                             None, prepared.cell_start, out)
+        ctx.save_for_backward(depth_c, rows, cells.point_cell)
+        ctx.rcb = (d, sp, tuple(feat.shape), feat.dtype, tuple(depth.shape), depth.dtype)
+        return out.permute(0, 4, 1, 2, 3) if channels_last else out
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        desc, sp, feat_shape, feat_dtype, depth_shape, depth_dtype = ctx.rcb
+        depth, rows, point_cell = ctx.saved_tensors
+        dev = depth.device
+        out_grad = out_grad.float()
+        desc = _lib.PoolDesc.from_buffer_copy(desc)
+        if out_grad.dim() == 5 and not out_grad.is_contiguous() and out_grad.permute(0, 2, 3, 4, 1).is_contiguous():
+            desc.layout = _lib.LAYOUT_CELLS_C            # rows in place
+        else:
+            out_grad = out_grad.contiguous()
+            desc.layout = _lib.LAYOUT_B_C_CELLS
+        depth_grad = torch.empty(depth.shape, dtype=torch.float32, device=dev)
+        feat_grad = torch.empty(rows.shape, dtype=torch.float32, device=dev)
+        gate = None
+        if desc.C in _strips.BWD_CHANNELS:
+            _strips.backward(sp, desc, out_grad, depth, rows, depth_grad, feat_grad)
+            gate = sp.status_tensor()
+        lib = _lib.lib()
+        ws_bytes = lib.rcb_pool_bwd_workspace_bytes(ctypes.byref(desc))
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        with _lib.launch_gate(gate):
+            _lib.check(lib.rcb_bev_pool_v2_bwd(
+                ctypes.byref(desc), _lib.ptr(out_grad), _lib.ptr(depth), _lib.ptr(rows), None, None, None,
+                _lib.ptr(point_cell), _lib.ptr(depth_grad), _lib.ptr(feat_grad), _lib.ptr(ws), ws_bytes, dev.index,
+                _lib.stream_ptr(dev)), "rcb_bev_pool_v2_bwd")
+        depth_grad, feat_grad = depth_grad.view(depth_shape), feat_grad.view(feat_shape)
+        return (depth_grad if depth_dtype == torch.float32 else depth_grad.to(depth_dtype),
+                feat_grad if feat_dtype == torch.float32 else feat_grad.to(feat_dtype), None, None, None)
+
+
+def _chain(cells, C, depth, feat, channels_last):
+    """The sort-free chain when it applies (mode, channel count, geometry), else None."""
+    if _strips.MODE != "chain" or C not in _strips.FWD_CHANNELS:
+        return None
+    # the gated fallback needs the two-level sort (its kernels take the launch gate): <= 1024 buckets of
+    # <= 2^12 cells
+    cps = cells.n_cells // max(cells.B, 1)
+    if cells.B * -(-cps // 4096) > 1024:
+        return None
+    sp = _strips.build(cells.point_cell, None, cells.n_img, cells.D, cells.H, cells.W, cells.n_cells)
+    if sp is None:
+        return None
+    return _ChainPool.apply(depth, feat.permute(0, 1, 3, 4, 2), cells, sp, channels_last)
+
+
+def _chain_wanted(C, return_prepared):
+    return _strips.MODE == "chain" and not return_prepared and C in _strips.FWD_CHANNELS
+
+
 def _collapse_z(bev):
     """view_transformer.py:203-204: (B, C, Z, Y, X) -> (B, C*Z, Y, X).  Z == 1 is a view (it keeps a
     channels-last result channels-last); the general case concatenates like the reference."""
@@ -91,6 +178,12 @@ def voxel_pooling_v2(coor, depth, feat, grid_lower_bound, grid_interval, grid_si
         else:
             bev = _bp.bev_pool_v2(depth, feat.permute(0, 1, 3, 4, 2), rd, rf, rb, (B, gz, gy, gx, C), st, ln)
         return torch.cat(bev.unbind(dim=2), 1) if collapse_z else bev
+    if _chain_wanted(C, return_prepared):
+        cells = point_cells_async(coor=coor, grid_lower_bound=grid_lower_bound, grid_interval=grid_interval,
+                                  grid_size=grid_size)
+        bev = _chain(cells, C, depth, feat, channels_last)
+        if bev is not None:
+            return _collapse_z(bev) if collapse_z else bev
     prepared = prepare_async(coor, grid_lower_bound, grid_interval, grid_size)
     feat = feat.permute(0, 1, 3, 4, 2)                       # view_transformer.py:195
     bev = _ViewPool.apply(depth, feat, prepared, channels_last)
@@ -106,6 +199,12 @@ def voxel_pooling_v2_from_calib(calib, axes, depth, feat, grid_lower_bound, grid
     pair, `axes` = frustum_axes(...); depth (B,N,D,H,W); feat (B,N,C,H,W).  The frustum points
     are generated inside the first prepare kernel; nothing of size P crosses PCIe or HBM as `coor`."""
     C = int(feat.shape[2])
+    if _chain_wanted(C, return_prepared):
+        cells = point_cells_async(calib=calib, axes=axes, grid_lower_bound=grid_lower_bound,
+                                  grid_interval=grid_interval, grid_size=grid_size, device=depth.device)
+        bev = _chain(cells, C, depth, feat, channels_last)
+        if bev is not None:
+            return _collapse_z(bev) if collapse_z else bev
     prepared = prepare_from_calib_async(calib, axes, grid_lower_bound, grid_interval, grid_size, device=depth.device)
     if not fused_path_supports(C):
         from .prepare import _finish
