@@ -10,6 +10,9 @@
 // their bit patterns) -- deterministic -- followed by one dense write kernel that produces all
 // three outputs, zeros included, with coalesced rows (no memset of the outputs, no per-pillar
 // host sync).
+#include <cstdlib>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace rcb {
@@ -26,6 +29,177 @@ __device__ __forceinline__ int rcs_radius(const float *rcs_row, int rcs_dim) {
   const float rad = __fadd_rn(t, 1.f);
   if (!(rad < 2147483520.f)) return 0x7fffff00;
   return (int)rad;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile (gather) form of the two maxima -- the default.  Both reductions are maxima over the pillars
+// whose window covers a cell, so a CELL can own them: a CTA takes a tile of 32 x 8R cells of one
+// sample, a thread R cells of one column, and the maxima live in registers -- no atomics, no L2
+// round trip per update, no memset, and heatmap / heatmap_feat / pillar_at leave as coalesced rows.
+//   k_radar_records : per pillar {x, y, radius, sample} (radius -1 = coordinates outside the grid)
+//                     + per sample the index range its pillars span (integer atomicMax: order-free)
+//   k_radar_tiles<R>: the CTA scans its sample's range of records in chunks of 1024, compacts the
+//                     pillars whose window meets the tile into shared memory (list order is
+//                     irrelevant: maxima), and every thread walks the list: |dx| <= r and |dy| <= r
+//                     is the clipped window of gaussian.py:40-47; G = float32(E_r[|dx|] * E_r[|dy|]),
+//                     the float64 product of the factors the splat kernel tabulates per pillar, comes
+//                     from a table over (radius, |dy|, |dx|) filled once per device (radii >= kTabR:
+//                     two exponentials, out of line).
+// Work: (cells x pillars near the tile) integer tests + one float64 product per covered cell, against
+// two L2 loads + up to two atomics per covered cell in the splat form (kept below for reference
+// measurements: RCB_RADAR_SPLAT=1).
+// ------------------------------------------------------------------------------------------------
+constexpr int kTabR = 64;  // tabulated radii / offsets: G[r][|dy|][|dx|], |dx|, |dy| <= r < kTabR
+// float32(E_r[|dy|] * E_r[|dx|]) with the eps cut of gaussian.py:21 applied: what a covered cell takes
+// the maximum of.  1 MB of address space, ~360 KB of it ever touched (offsets <= r): L1 / L2 resident.
+__device__ float g_radar_tab[kTabR * kTabR * kTabR];
+
+__device__ __forceinline__ double radar_denom(int radius) {
+  // gaussian.py:17-23 with sigma = diameter / 6 (gaussian.py:38-39), all float64
+  const double diameter = 2.0 * (double)radius + 1.0;
+  const double sigma = diameter / 6.0;
+  return 2.0 * sigma * sigma;
+}
+__device__ __forceinline__ double radar_factor(int k, double denom) {
+  return exp(-(double)((long long)k * k) / denom);
+}
+__device__ __forceinline__ float radar_value(double ex, double ey) {
+  double g = ex * ey;
+  if (g < 2.220446049250313e-16) g = 0.0;  // np.finfo(float64).eps * h.max(), h.max() == 1
+  return (float)g;
+}
+// radii beyond the table (rare): kept out of line so that the float64 division and exponentials stay
+// off the tile kernel's hot loop
+__device__ __noinline__ float radar_value_big(int ax, int ay, int radius) {
+  const double denom = radar_denom(radius);
+  return radar_value(radar_factor(ax, denom), radar_factor(ay, denom));
+}
+
+__global__ void __launch_bounds__(256) k_radar_table() {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kTabR * kTabR * kTabR) return;
+  const int r = i / (kTabR * kTabR), ay = (i / kTabR) % kTabR, ax = i % kTabR;
+  if (ax > r || ay > r) return;
+  const double denom = radar_denom(r);
+  g_radar_tab[i] = radar_value(radar_factor(ax, denom), radar_factor(ay, denom));
+}
+
+// range[2b] = max(V - v), range[2b + 1] = max(v + 1) over the valid pillars of sample b (zeroed before)
+__global__ void __launch_bounds__(256) k_radar_records(RadarParams p, const float *__restrict__ rcs,
+                                                       const int *__restrict__ coors, int4 *__restrict__ rec,
+                                                       int *__restrict__ range) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  int4 q = make_int4(0, 0, -1, -1);
+  if (v < p.V) {
+    const int4 c = __ldg(reinterpret_cast<const int4 *>(coors) + v);  // [b, z, y, x]
+    if (c.x >= 0 && c.x < p.B && c.z >= 0 && c.z < p.ny && c.w >= 0 && c.w < p.nx)
+      q = make_int4(c.w, c.z, rcs_radius(rcs + (size_t)v * p.rcs_dim, p.rcs_dim), c.x);
+    rec[v] = q;
+  }
+  // one pair of atomics per run of equal samples inside the warp (pillars arrive grouped by sample:
+  // usually one run); lanes without a valid pillar carry sample -1
+  const int lane = lane_id();
+  const int prev = __shfl_up_sync(kFull, q.w, 1);
+  const unsigned heads = __ballot_sync(kFull, lane == 0 || prev != q.w);
+  if ((heads >> lane) & 1u) {
+    const unsigned after = heads & ~((2u << lane) - 1u);          // heads above this lane
+    const int run_last = after ? __ffs(after) - 2 : 31;           // last lane of this run
+    if (q.w >= 0) {
+      atomicMax(range + 2 * q.w, p.V - v);                        // v ascends with the lane: the head has the smallest
+      atomicMax(range + 2 * q.w + 1, v + (run_last - lane) + 1);  // ... and the run's last lane the largest
+    }
+  }
+}
+
+constexpr int kScanPerThread = 4;                    // records a thread inspects per round
+constexpr int kScanChunk = 256 * kScanPerThread;     // = capacity of the CTA's pillar lists
+
+template <int R>
+__global__ void __launch_bounds__(256) k_radar_tiles(RadarParams p, const float *__restrict__ rcs,
+                                                     const int4 *__restrict__ rec, const int *__restrict__ range,
+                                                     int *__restrict__ pillar_at, float *__restrict__ heatmap,
+                                                     float *__restrict__ heatmap_feat, int tiles_x, int tiles_y) {
+  __shared__ int4 s_list[kScanChunk];
+  __shared__ int s_own[R * 256];  // pillar at each cell of the tile (index + 1), thread-major like the registers
+  __shared__ int s_n, s_nbig;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / (tiles_x * tiles_y), t = blockIdx.x % (tiles_x * tiles_y);
+  const int x0 = (t % tiles_x) * 32, y0 = (t / tiles_x) * (8 * R);
+  const int x1 = min(x0 + 31, p.nx - 1), y1 = min(y0 + 8 * R - 1, p.ny - 1);
+  const int v_lo = p.V - range[2 * b], v_hi = range[2 * b + 1];  // empty sample: v_lo = V, v_hi = 0
+  const int cx = x0 + lane, cy = y0 + warp;                      // cell j of the thread: (cx, cy + 8j)
+  float best[R];
+  int last[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) best[j] = 0.f, last[j] = 0, s_own[j * 256 + tid] = 0;
+
+  for (int v0 = v_lo; v0 < v_hi; v0 += kScanChunk) {
+    __syncthreads();  // the previous chunk's list is no longer read (first trip: s_own is zeroed)
+    if (tid == 0) s_n = 0, s_nbig = 0;
+    __syncthreads();
+    int4 q[kScanPerThread];
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) {
+      const int v = v0 + k * 256 + tid;
+      q[k] = v < v_hi ? __ldg(rec + v) : make_int4(0, 0, -1, -1);
+    }
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) {
+      // the window [x - r, x + r] x [y - r, y + r] meets the tile
+      const int ddx = q[k].x - min(max(q[k].x, x0), x1), ddy = q[k].y - min(max(q[k].y, y0), y1);
+      if (q[k].w == b && q[k].z >= 0 && abs(ddx) <= q[k].z && abs(ddy) <= q[k].z) {
+        const int v1 = v0 + k * 256 + tid + 1;
+        // small radii fill the list from the front, radii beyond the table from the back
+        if (q[k].z < kTabR) s_list[atomicAdd(&s_n, 1)] = make_int4(q[k].x, q[k].y, q[k].z << 12, v1);
+        else s_list[kScanChunk - 1 - atomicAdd(&s_nbig, 1)] = make_int4(q[k].x, q[k].y, q[k].z, v1);
+        if ((ddx | ddy) == 0) {  // the pillar's own cell is in this tile
+          const int ly = q[k].y - y0;
+          atomicMax(&s_own[(ly >> 3) * 256 + (ly & 7) * 32 + (q[k].x - x0)], v1);
+        }
+      }
+    }
+    __syncthreads();
+    const int n = s_n;
+    for (int i = 0; i < n; ++i) {
+      const int4 e = s_list[i];                      // x, y, radius << 12, index + 1
+      const unsigned ax = (unsigned)abs(cx - e.x);
+      const unsigned r6 = (unsigned)e.z >> 6;        // radius << 6: compares against offsets << 6
+      const bool in_x = (ax << 6) <= r6;
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const unsigned ay6 = (unsigned)abs(cy + 8 * j - e.y) << 6;
+        if (in_x && ay6 <= r6) {                     // the row test is warp-uniform
+          best[j] = fmaxf(best[j], __ldg(g_radar_tab + ((unsigned)e.z + ay6 + ax)));
+          last[j] = max(last[j], e.w);
+        }
+      }
+    }
+    const int nbig = s_nbig;
+    for (int i = 0; i < nbig; ++i) {
+      const int4 e = s_list[kScanChunk - 1 - i];
+      const int ax = abs(cx - e.x);
+      if (ax > e.z) continue;
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const int ay = abs(cy + 8 * j - e.y);
+        if (ay > e.z) continue;
+        best[j] = fmaxf(best[j], radar_value_big(ax, ay, e.z));
+        last[j] = max(last[j], e.w);
+      }
+    }
+  }
+  __syncthreads();  // (no trip at all: s_own zeroed by its own thread, no barrier needed, but harmless)
+  if (cx >= p.nx) return;
+  const int col = p.rcs_dim - 2;
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int y = cy + 8 * j;
+    if (y >= p.ny) break;
+    const size_t g = (size_t)b * p.cells + (size_t)y * p.nx + cx;
+    pillar_at[g] = s_own[j * 256 + tid];
+    st_stream_f32(heatmap + g, best[j]);
+    st_stream_f32(heatmap_feat + g, last[j] > 0 ? __ldg(rcs + (size_t)(last[j] - 1) * p.rcs_dim + col) : 0.f);
+  }
 }
 
 // Splat: one CTA per group of kSplatPillars pillars; for each pillar the ROWS of its window are dealt
@@ -140,7 +314,9 @@ __global__ void __launch_bounds__(256)
   if (cell >= p.cells) return;
   const size_t g = (size_t)b * p.cells + cell;
   const int4 own = *reinterpret_cast<const int4 *>(pillar_at + g);  // (stored + 1: 0 = no pillar)
-  if (warp == 0) {
+  if (heat_bits == nullptr) {
+    // heatmap / heatmap_feat were written by k_radar_tiles
+  } else if (warp == 0) {
     const int4 hb = *reinterpret_cast<const int4 *>(heat_bits + g);
     st_stream_f4(reinterpret_cast<float4 *>(heatmap + g),
                  make_float4(__int_as_float(hb.x), __int_as_float(hb.y), __int_as_float(hb.z), __int_as_float(hb.w)));
@@ -187,9 +363,11 @@ __global__ void __launch_bounds__(256)
     if (threadIdx.x < n) {
       const int g = b * p.cells + cell0 + threadIdx.x;
       o = pillar_at[g] - 1;  // (stored + 1: 0 = no pillar)
-      heatmap[g] = __int_as_float(heat_bits[g]);
-      const int lc = last_cover[g] - 1;
-      heatmap_feat[g] = lc >= 0 ? __ldg(rcs + (size_t)lc * p.rcs_dim + p.rcs_dim - 2) : 0.f;
+      if (heat_bits != nullptr) {
+        heatmap[g] = __int_as_float(heat_bits[g]);
+        const int lc = last_cover[g] - 1;
+        heatmap_feat[g] = lc >= 0 ? __ldg(rcs + (size_t)lc * p.rcs_dim + p.rcs_dim - 2) : 0.f;
+      }
     }
     s_owner[threadIdx.x] = o;
   }
@@ -233,10 +411,47 @@ static int fill_radar(const rcb_radar_desc *d, RadarParams *p) {
 
 using namespace rcb;
 
+struct RadarWorkspace {
+  size_t plane, off_rec, off_range, total;
+};
+static RadarWorkspace radar_workspace(const RadarParams &p) {
+  RadarWorkspace w;
+  w.plane = align_up((size_t)p.B * p.cells * 4, 256);
+  w.off_rec = w.plane;                                                      // tile form: pillar_at | records | ranges
+  w.off_range = w.off_rec + align_up((size_t)max(p.V, 1) * 16, 256);
+  const size_t tiles_total = w.off_range + align_up((size_t)p.B * 8, 256);
+  w.total = tiles_total > 3 * w.plane ? tiles_total : 3 * w.plane;         // splat form: three planes
+  return w;
+}
+
 extern "C" size_t rcb_radar_workspace_bytes(const rcb_radar_desc *d) {
   RadarParams p;
   if (fill_radar(d, &p) != RCB_OK) return 0;
-  return 3 * align_up((size_t)p.B * p.cells * 4, 256);
+  return radar_workspace(p).total;
+}
+
+// the (radius, offset) table of the tile kernel: filled once per device
+static int radar_table_ready(int device, cudaStream_t s) {
+  static std::mutex mu;
+  static bool done[64];
+  int dev = device;
+  if (dev < 0) RCB_CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 64 && done[dev]) return RCB_OK;
+  k_radar_table<<<ceil_div(kTabR * kTabR * kTabR, 256), 256, 0, s>>>();
+  RCB_LAUNCH_CHECK();
+  if (dev < 64) done[dev] = true;
+  return RCB_OK;
+}
+
+template <int R>
+static int launch_radar_tiles(const RadarParams &p, const float *rcs, const int4 *rec, const int *range, int *pillar_at,
+                              float *heatmap, float *heatmap_feat, cudaStream_t s) {
+  const int tiles_x = ceil_div(p.nx, 32), tiles_y = ceil_div(p.ny, 8 * R);
+  k_radar_tiles<R><<<(unsigned)(p.B * tiles_x * tiles_y), 256, 0, s>>>(p, rcs, rec, range, pillar_at, heatmap,
+                                                                      heatmap_feat, tiles_x, tiles_y);
+  RCB_LAUNCH_CHECK();
+  return RCB_OK;
 }
 
 extern "C" int rcb_radar_rcs_scatter(const rcb_radar_desc *d, const float *point_features,
@@ -248,19 +463,46 @@ extern "C" int rcb_radar_rcs_scatter(const rcb_radar_desc *d, const float *point
   if (rc != RCB_OK) return rc;
   if (!features || !heatmap || !heatmap_feat || !workspace) return RCB_ERR_ARG;
   if (p.V > 0 && (!point_features || !rcs || !coors)) return RCB_ERR_ARG;
-  const size_t plane = align_up((size_t)p.B * p.cells * 4, 256);
-  if (workspace_bytes < 3 * plane) return RCB_ERR_WORKSPACE;
+  const RadarWorkspace w = radar_workspace(p);
+  if (workspace_bytes < w.total) return RCB_ERR_WORKSPACE;
   DeviceGuard guard(device);
   if (guard.err) return guard.err;
   cudaStream_t s = (cudaStream_t)stream;
   char *ws = static_cast<char *>(workspace);
-  int *pillar_at = (int *)ws, *last_cover = (int *)(ws + plane), *heat_bits = (int *)(ws + 2 * plane);
-  RCB_CUDA_TRY(cudaMemsetAsync(ws, 0, 3 * plane, s));  // indices are stored + 1, heat as bit patterns: 0 = nothing
+  int *pillar_at = (int *)ws;
   const int sms = sm_count_cached(device);
-  if (p.V > 0) {
-    k_radar_splat<<<max(1, min(ceil_div(p.V, kSplatPillars), sms * 16)), 256, 0, s>>>(p, rcs, coors, pillar_at,
-                                                                                     last_cover, heat_bits);
-    RCB_LAUNCH_CHECK();
+  const char *force_splat = getenv("RCB_RADAR_SPLAT");
+  const bool tiles = !(force_splat && force_splat[0] == '1') && (((uintptr_t)coors | (uintptr_t)workspace) % 16) == 0 &&
+                     (long long)p.B * ceil_div(p.nx, 32) * ceil_div(p.ny, 8) < (1ll << 31) && p.nx < (1 << 24) && p.ny < (1 << 24);
+  const int *last_cover = nullptr, *heat_bits = nullptr;
+  if (tiles) {
+    int4 *rec = (int4 *)(ws + w.off_rec);
+    int *range = (int *)(ws + w.off_range);
+    rc = radar_table_ready(device, s);
+    if (rc != RCB_OK) return rc;
+    RCB_CUDA_TRY(cudaMemsetAsync(range, 0, (size_t)p.B * 8, s));
+    if (p.V > 0) {
+      k_radar_records<<<ceil_div(p.V, 256), 256, 0, s>>>(p, rcs, coors, rec, range);
+      RCB_LAUNCH_CHECK();
+    }
+    // rows per thread: the fewest for which the grid stays within ~16 CTAs per SM (every CTA scans its
+    // sample's records once; measured at 512^2, B = 8: R = 8 161 us per call, R = 4 148, R = 2 149, R = 1 170)
+    const long long base = (long long)p.B * ceil_div(p.nx, 32);
+    long long budget = (long long)sms * 16;
+    if (const char *e = getenv("RCB_RADAR_BUDGET")) budget = (long long)sms * atoi(e);  // development knob
+    if (base * ceil_div(p.ny, 8) <= budget) rc = launch_radar_tiles<1>(p, rcs, rec, range, pillar_at, heatmap, heatmap_feat, s);
+    else if (base * ceil_div(p.ny, 16) <= budget) rc = launch_radar_tiles<2>(p, rcs, rec, range, pillar_at, heatmap, heatmap_feat, s);
+    else if (base * ceil_div(p.ny, 32) <= budget) rc = launch_radar_tiles<4>(p, rcs, rec, range, pillar_at, heatmap, heatmap_feat, s);
+    else rc = launch_radar_tiles<8>(p, rcs, rec, range, pillar_at, heatmap, heatmap_feat, s);
+    if (rc != RCB_OK) return rc;
+  } else {
+    int *lc = (int *)(ws + w.plane), *hb = (int *)(ws + 2 * w.plane);
+    RCB_CUDA_TRY(cudaMemsetAsync(ws, 0, 3 * w.plane, s));  // indices are stored + 1, heat as bit patterns: 0 = nothing
+    if (p.V > 0) {
+      k_radar_splat<<<max(1, min(ceil_div(p.V, kSplatPillars), sms * 16)), 256, 0, s>>>(p, rcs, coors, pillar_at, lc, hb);
+      RCB_LAUNCH_CHECK();
+    }
+    last_cover = lc, heat_bits = hb;
   }
   if (p.cells % 4 == 0 && (((uintptr_t)features | (uintptr_t)heatmap | (uintptr_t)heatmap_feat | (uintptr_t)workspace) % 16) == 0) {
     k_radar_write4<<<p.B * ceil_div(p.cells, 128), 256, 0, s>>>(p, point_features, rcs, pillar_at, last_cover, heat_bits,

@@ -81,8 +81,8 @@ def lss_view_transform(x, n_cams, D, C, calib, axes, grid_lower_bound, grid_inte
     x (B*N, D + C, H, W); calib = get_lidar_coor's six tensors (or a packed pair from pack_calib);
     axes = frustum_axes(...).  Returns (bev_feat, depth) like the reference: bev_feat (B, C*Z, Y, X)
     (collapse_z) and depth (B*N, D, H, W)."""
-    from .prepare import prepare_from_calib_async
-    from .view_pool import _ViewPool, _collapse_z, fused_path_supports
+    from .prepare import point_cells_async, prepare_from_calib_async
+    from .view_pool import _ViewPool, _chain, _chain_wanted, _collapse_z, fused_path_supports
     if not fused_path_supports(C):
         raise ValueError(f"lss_view_transform needs C % 4 == 0 (C % 8 above 128 channels, C <= 256), got {C}")
     bn, _, H, W = x.shape
@@ -90,6 +90,13 @@ def lss_view_transform(x, n_cams, D, C, calib, axes, grid_lower_bound, grid_inte
         raise ValueError("x.shape[0] must be B * n_cams")
     B = bn // n_cams
     depth, ctx_cl = depth_context_split(x, D, C)
+    bev = None
+    if _chain_wanted(C, False):                                 # strips mode "chain": pool without sorting
+        cells = point_cells_async(calib=calib, axes=axes, grid_lower_bound=grid_lower_bound,
+                                  grid_interval=grid_interval, grid_size=grid_size, device=x.device)
+        bev = _chain(cells, C, depth.view(B, n_cams, D, H, W), ctx_cl.view(B, n_cams, H, W, C), channels_last)
+    if bev is not None:
+        return (_collapse_z(bev) if collapse_z else bev), depth
     prepared = prepare_from_calib_async(calib, axes, grid_lower_bound, grid_interval, grid_size, device=x.device)
     bev = _ViewPool.apply(depth.view(B, n_cams, D, H, W), ctx_cl.view(B, n_cams, H, W, C), prepared, channels_last)
     if collapse_z:

@@ -125,7 +125,8 @@ class _ChainPool(torch.autograd.Function):
 
 
 def _chain(cells, C, depth, feat, channels_last):
-    """The sort-free chain when it applies (mode, channel count, geometry), else None."""
+    """The sort-free chain when it applies (mode, channel count, geometry), else None.  `feat` is the
+    (B, N, H, W, C) view the pooling operators take (view_transformer.py:195)."""
     if _strips.MODE != "chain" or C not in _strips.FWD_CHANNELS:
         return None
     # the gated fallback needs the two-level sort (its kernels take the launch gate): <= 1024 buckets of
@@ -136,7 +137,7 @@ def _chain(cells, C, depth, feat, channels_last):
     sp = _strips.build(cells.point_cell, None, cells.n_img, cells.D, cells.H, cells.W, cells.n_cells)
     if sp is None:
         return None
-    return _ChainPool.apply(depth, feat.permute(0, 1, 3, 4, 2), cells, sp, channels_last)
+    return _ChainPool.apply(depth, feat, cells, sp, channels_last)
 
 
 def _chain_wanted(C, return_prepared):
@@ -181,7 +182,7 @@ def voxel_pooling_v2(coor, depth, feat, grid_lower_bound, grid_interval, grid_si
     if _chain_wanted(C, return_prepared):
         cells = point_cells_async(coor=coor, grid_lower_bound=grid_lower_bound, grid_interval=grid_interval,
                                   grid_size=grid_size)
-        bev = _chain(cells, C, depth, feat, channels_last)
+        bev = _chain(cells, C, depth, feat.permute(0, 1, 3, 4, 2), channels_last)
         if bev is not None:
             return _collapse_z(bev) if collapse_z else bev
     prepared = prepare_async(coor, grid_lower_bound, grid_interval, grid_size)
@@ -202,7 +203,7 @@ def voxel_pooling_v2_from_calib(calib, axes, depth, feat, grid_lower_bound, grid
     if _chain_wanted(C, return_prepared):
         cells = point_cells_async(calib=calib, axes=axes, grid_lower_bound=grid_lower_bound,
                                   grid_interval=grid_interval, grid_size=grid_size, device=depth.device)
-        bev = _chain(cells, C, depth, feat, channels_last)
+        bev = _chain(cells, C, depth, feat.permute(0, 1, 3, 4, 2), channels_last)
         if bev is not None:
             return _collapse_z(bev) if collapse_z else bev
     prepared = prepare_from_calib_async(calib, axes, grid_lower_bound, grid_interval, grid_size, device=depth.device)
