@@ -49,10 +49,14 @@ __device__ __forceinline__ int rcs_radius(const float *rcs_row, int rcs_dim) {
 // two L2 loads + up to two atomics per covered cell in the splat form (kept below for reference
 // measurements: RCB_RADAR_SPLAT=1).
 // ------------------------------------------------------------------------------------------------
-constexpr int kTabR = 64;  // tabulated radii / offsets: G[r][|dy|][|dx|], |dx|, |dy| <= r < kTabR
-// float32(E_r[|dy|] * E_r[|dx|]) with the eps cut of gaussian.py:21 applied: what a covered cell takes
-// the maximum of.  1 MB of address space, ~360 KB of it ever touched (offsets <= r): L1 / L2 resident.
-__device__ float g_radar_tab[kTabR * kTabR * kTabR];
+constexpr int kTabR = 64;  // tabulated radii / offsets: G[r][|dy|][|dx|], r, |dx|, |dy| < kTabR
+// float32(E_r[|dy|] * E_r[|dx|]) with the eps cut of gaussian.py:21 applied -- what a covered cell takes
+// the maximum of -- and EXACTLY ZERO outside the window (|dx| > r or |dy| > r).  Inside the window the
+// value is never zero (its minimum, at the corners, is exp(-36 r^2 / (2r+1)^2) > exp(-9)), so
+// "value > 0" IS the window test: the hot loop needs no comparison against the radius.  1 MB, L2
+// resident, the part within reach of the common radii L1 resident.
+constexpr int kTabStride = kTabR * kTabR + 1;  // per radius: the 64 x 64 offsets + one zero that out-of-table offsets clamp to
+__device__ float g_radar_tab[kTabR * kTabStride];
 
 __device__ __forceinline__ double radar_denom(int radius) {
   // gaussian.py:17-23 with sigma = diameter / 6 (gaussian.py:38-39), all float64
@@ -77,11 +81,10 @@ __device__ __noinline__ float radar_value_big(int ax, int ay, int radius) {
 
 __global__ void __launch_bounds__(256) k_radar_table() {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= kTabR * kTabR * kTabR) return;
-  const int r = i / (kTabR * kTabR), ay = (i / kTabR) % kTabR, ax = i % kTabR;
-  if (ax > r || ay > r) return;
+  if (i >= kTabR * kTabStride) return;
+  const int r = i / kTabStride, o = i % kTabStride, ay = o / kTabR, ax = o % kTabR;
   const double denom = radar_denom(r);
-  g_radar_tab[i] = radar_value(radar_factor(ax, denom), radar_factor(ay, denom));
+  g_radar_tab[i] = (ax > r || ay > r) ? 0.f : radar_value(radar_factor(ax, denom), radar_factor(ay, denom));  // o == 4096: ay = 64 > r
 }
 
 // range[2b] = max(V - v), range[2b + 1] = max(v + 1) over the valid pillars of sample b (zeroed before)
@@ -118,7 +121,8 @@ template <int R>
 __global__ void __launch_bounds__(256) k_radar_tiles(RadarParams p, const float *__restrict__ rcs,
                                                      const int4 *__restrict__ rec, const int *__restrict__ range,
                                                      int *__restrict__ pillar_at, float *__restrict__ heatmap,
-                                                     float *__restrict__ heatmap_feat, int tiles_x, int tiles_y) {
+                                                     float *__restrict__ heatmap_feat, int tiles_x, int tiles_y,
+                                                     const float *__restrict__ table) {
   __shared__ int4 s_list[kScanChunk];
   __shared__ int s_own[R * 256];  // pillar at each cell of the tile (index + 1), thread-major like the registers
   __shared__ int s_n, s_nbig;
@@ -128,6 +132,7 @@ __global__ void __launch_bounds__(256) k_radar_tiles(RadarParams p, const float 
   const int x1 = min(x0 + 31, p.nx - 1), y1 = min(y0 + 8 * R - 1, p.ny - 1);
   const int v_lo = p.V - range[2 * b], v_hi = range[2 * b + 1];  // empty sample: v_lo = V, v_hi = 0
   const int cx = x0 + lane, cy = y0 + warp;                      // cell j of the thread: (cx, cy + 8j)
+  const int cy64 = cy << 6;
   float best[R];
   int last[R];
 #pragma unroll
@@ -150,7 +155,7 @@ __global__ void __launch_bounds__(256) k_radar_tiles(RadarParams p, const float 
       if (q[k].w == b && q[k].z >= 0 && abs(ddx) <= q[k].z && abs(ddy) <= q[k].z) {
         const int v1 = v0 + k * 256 + tid + 1;
         // small radii fill the list from the front, radii beyond the table from the back
-        if (q[k].z < kTabR) s_list[atomicAdd(&s_n, 1)] = make_int4(q[k].x, q[k].y, q[k].z << 12, v1);
+        if (q[k].z < kTabR) s_list[atomicAdd(&s_n, 1)] = make_int4(q[k].x, q[k].y << 6, q[k].z * kTabStride, v1);
         else s_list[kScanChunk - 1 - atomicAdd(&s_nbig, 1)] = make_int4(q[k].x, q[k].y, q[k].z, v1);
         if ((ddx | ddy) == 0) {  // the pillar's own cell is in this tile
           const int ly = q[k].y - y0;
@@ -161,17 +166,17 @@ __global__ void __launch_bounds__(256) k_radar_tiles(RadarParams p, const float 
     __syncthreads();
     const int n = s_n;
     for (int i = 0; i < n; ++i) {
-      const int4 e = s_list[i];                      // x, y, radius << 12, index + 1
-      const unsigned ax = (unsigned)abs(cx - e.x);
-      const unsigned r6 = (unsigned)e.z >> 6;        // radius << 6: compares against offsets << 6
-      const bool in_x = (ax << 6) <= r6;
+      const int4 e = s_list[i];                      // x, y << 6, radius * kTabStride, index + 1
+      const unsigned ax = __sad(cx, e.x, 0u);        // |dx|
 #pragma unroll
       for (int j = 0; j < R; ++j) {
-        const unsigned ay6 = (unsigned)abs(cy + 8 * j - e.y) << 6;
-        if (in_x && ay6 <= r6) {                     // the row test is warp-uniform
-          best[j] = fmaxf(best[j], __ldg(g_radar_tab + ((unsigned)e.z + ay6 + ax)));
-          last[j] = max(last[j], e.w);
-        }
+        const unsigned off = __sad(cy64 + 512 * j, e.y, ax);   // |dy| * 64 + |dx|
+        // offsets outside the table (|dx| or |dy| >= 64) read the radius' zero entry: no branch, the loads
+        // of an unrolled trip stay in flight together
+        const unsigned o = (ax < kTabR && off < kTabR * kTabR) ? off : (unsigned)(kTabR * kTabR);
+        const float g = __ldg(table + ((unsigned)e.z + o));
+        best[j] = fmaxf(best[j], g);
+        if (g > 0.f) last[j] = max(last[j], e.w);    // inside the window (see g_radar_tab)
       }
     }
     const int nbig = s_nbig;
@@ -438,7 +443,7 @@ static int radar_table_ready(int device, cudaStream_t s) {
   if (dev < 0) RCB_CUDA_TRY(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lock(mu);
   if (dev < 64 && done[dev]) return RCB_OK;
-  k_radar_table<<<ceil_div(kTabR * kTabR * kTabR, 256), 256, 0, s>>>();
+  k_radar_table<<<ceil_div(kTabR * kTabStride, 256), 256, 0, s>>>();
   RCB_LAUNCH_CHECK();
   if (dev < 64) done[dev] = true;
   return RCB_OK;
@@ -448,8 +453,10 @@ template <int R>
 static int launch_radar_tiles(const RadarParams &p, const float *rcs, const int4 *rec, const int *range, int *pillar_at,
                               float *heatmap, float *heatmap_feat, cudaStream_t s) {
   const int tiles_x = ceil_div(p.nx, 32), tiles_y = ceil_div(p.ny, 8 * R);
+  float *table = nullptr;
+  RCB_CUDA_TRY(cudaGetSymbolAddress((void **)&table, g_radar_tab));
   k_radar_tiles<R><<<(unsigned)(p.B * tiles_x * tiles_y), 256, 0, s>>>(p, rcs, rec, range, pillar_at, heatmap,
-                                                                      heatmap_feat, tiles_x, tiles_y);
+                                                                      heatmap_feat, tiles_x, tiles_y, table);
   RCB_LAUNCH_CHECK();
   return RCB_OK;
 }
