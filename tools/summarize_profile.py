@@ -36,7 +36,8 @@ def to_bytes(v, u):
 seen = {}
 lines = [f"# ncu --set full summary, tag {tag}", "",
          "One launch per kernel (first occurrence after warm-up), `--clock-control none`, B=8 R50 workload "
-         "(`bench.py --steps 3 --warmup 3`).  Times under ncu are cold-cache and serialised: compare shares.", ""]
+         "(`bench.py --steps 3 --warmup 3`; tags r02radar / r02chain: `tools/radar_times.py` / "
+         "`tools/chain_step.py chain`).  Times under ncu are cold-cache and serialised: compare shares.", ""]
 for d in data:
     name = d[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("rcb::", "")
     if name in seen:
@@ -58,6 +59,10 @@ for d in data:
     lines.append("")
 with open(os.path.join(out_dir, f"{tag}_ncu_kernels.md"), "w") as f:
     f.write("\n".join(lines) + "\n")
+
+if "--kernels-only" in sys.argv:   # captures of other programs (radar, the sort-free chain): per-kernel summary only
+    print(open(os.path.join(out_dir, f"{tag}_ncu_kernels.md")).read()[:400])
+    sys.exit(0)
 
 # DRAM traffic per launch, grouped by bench.py stage
 # bench.py's roofline is quoted on ONE kernel: "fwd" = k_fwd_cells, "bwd" = k_pool_bwd_pixels16
