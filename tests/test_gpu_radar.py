@@ -101,3 +101,62 @@ def test_config4_full_size_properties_and_timing(ny, capsys):
     with capsys.disabled():
         print(f"\n[timing] radar RCS scatter B=8 V={pf.shape[0]} grid {ny}x{ny}: {ms * 1e3:.1f} us, "
               f"{out_bytes / ms / 1e6:.0f} GB/s algorithmic ({B / ms * 1e3:.0f} samples/s)")
+
+
+def _edge_case(seed, B, ny, nx, n_per_sample, rcs_hi, cin=8, drop_sample=None):
+    """Pillars in arbitrary order (samples interleaved), radii up to relu(rcs_hi * 2) + 1, unique cells
+    per sample."""
+    g = torch.Generator().manual_seed(seed)
+    feats, rcss, coors = [], [], []
+    for b in range(B):
+        if b == drop_sample:
+            continue
+        lin = torch.randperm(ny * nx, generator=g)[:n_per_sample]
+        r = torch.zeros(n_per_sample, 7)
+        r[:, 0] = torch.rand(n_per_sample, generator=g)
+        r[:, 1] = torch.rand(n_per_sample, generator=g)
+        r[:, 5] = torch.rand(n_per_sample, generator=g) * (rcs_hi + 5.0) - 5.0
+        c = torch.zeros(n_per_sample, 4, dtype=torch.int32)
+        c[:, 0] = b
+        c[:, 2] = (lin // nx).int()
+        c[:, 3] = (lin % nx).int()
+        feats.append(torch.randn(n_per_sample, cin, generator=g))
+        rcss.append(r)
+        coors.append(c)
+    pf, rc, co = torch.cat(feats), torch.cat(rcss), torch.cat(coors)
+    perm = torch.randperm(pf.shape[0], generator=g)          # samples interleaved
+    return pf[perm].contiguous(), rc[perm].contiguous(), co[perm].contiguous()
+
+
+@pytest.mark.parametrize("B,ny,nx,n,rcs_hi,drop", [
+    (3, 100, 176, 60, 30.0, None),     # ragged tiles (nx, ny not multiples of 32 / 8), radii <= 61
+    (2, 200, 176, 40, 120.0, None),    # radii up to ~240: beyond the table (>= 64), windows larger than the grid
+    (4, 64, 64, 50, 30.0, 2),          # a sample without pillars
+    (1, 40, 520, 30, 60.0, None),      # wide grid: several rows per thread at small batch
+])
+def test_tile_form_edge_cases_against_oracle(B, ny, nx, n, rcs_hi, drop):
+    """The tile (gather) kernels on what the goldens do not cover: pillars in arbitrary order, radii
+    beyond the tabulated range, an empty sample, ragged tile borders.  features / heatmap_feat
+    bit-exact, heatmap <= 1 ulp (fp32)."""
+    import rcbevdet_b200 as rcb
+    pf, rc, co = _edge_case(7 + B, B, ny, nx, n, rcs_hi, drop_sample=drop)
+    wf, wh, whf = oracle.radar_rcs_scatter(pf.numpy(), rc.numpy(), co.numpy(), B, ny, nx)
+    f, h, hf = rcb.radar_rcs_scatter(pf.cuda(), rc.cuda(), co.cuda(), B, ny, nx)
+    assert np.array_equal(f.cpu().numpy(), wf)
+    assert np.array_equal(hf.cpu().numpy(), whf)
+    assert _ulp_close(h.cpu().numpy(), wh)
+    if drop is not None:
+        assert float(h[drop].abs().max()) == 0.0 and float(f[drop].abs().max()) == 0.0
+
+
+def test_tile_and_splat_forms_agree(monkeypatch):
+    """RCB_RADAR_SPLAT=1 selects the scatter kernels (kept for reference measurements): same
+    features / heatmap_feat bits, heat-map within 1 ulp of the tile form."""
+    import rcbevdet_b200 as rcb
+    from rcbevdet_b200 import rig
+    pf, rc, co = (t.cuda() for t in rig.radar_pillars(2, 128, 128, points_per_sample=800, seed=9))
+    a = rcb.radar_rcs_scatter(pf, rc, co, 2, 128, 128)
+    monkeypatch.setenv("RCB_RADAR_SPLAT", "1")
+    b = rcb.radar_rcs_scatter(pf, rc, co, 2, 128, 128)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
+    assert _ulp_close(a[1].cpu().numpy(), b[1].cpu().numpy())
