@@ -122,7 +122,9 @@ __global__ void __launch_bounds__(256) k_radar_tiles(RadarParams p, const float 
                                                      const int4 *__restrict__ rec, const int *__restrict__ range,
                                                      int *__restrict__ pillar_at, float *__restrict__ heatmap,
                                                      float *__restrict__ heatmap_feat, int tiles_x, int tiles_y,
-                                                     const float *__restrict__ table) {
+                                                     const float *__restrict__ table,
+                                                     const float *__restrict__ point_features,
+                                                     float *__restrict__ features) {
   __shared__ int4 s_list[kScanChunk];
   __shared__ int s_own[R * 256];  // pillar at each cell of the tile (index + 1), thread-major like the registers
   __shared__ int s_n, s_nbig;
@@ -201,7 +203,17 @@ __global__ void __launch_bounds__(256) k_radar_tiles(RadarParams p, const float 
     const int y = cy + 8 * j;
     if (y >= p.ny) break;
     const size_t g = (size_t)b * p.cells + (size_t)y * p.nx + cx;
-    pillar_at[g] = s_own[j * 256 + tid];
+    const int own = s_own[j * 256 + tid];
+    if (features != nullptr) {
+      // small grids: the dense feature planes leave from here too (a warp writes 128-byte rows of one
+      // channel; the pillar's row of point_features is 2 cache lines, read once and served from L1)
+      float *dst = features + (size_t)b * p.Cin * p.cells + (size_t)y * p.nx + cx;
+      const float *src = point_features + (size_t)(own > 0 ? own - 1 : 0) * p.Cin;
+#pragma unroll 8
+      for (int c = 0; c < p.Cin; ++c) st_stream_f32(dst + (size_t)c * p.cells, own > 0 ? __ldg(src + c) : 0.f);
+    } else {
+      pillar_at[g] = own;
+    }
     st_stream_f32(heatmap + g, best[j]);
     st_stream_f32(heatmap_feat + g, last[j] > 0 ? __ldg(rcs + (size_t)(last[j] - 1) * p.rcs_dim + col) : 0.f);
   }
@@ -451,12 +463,14 @@ static int radar_table_ready(int device, cudaStream_t s) {
 
 template <int R>
 static int launch_radar_tiles(const RadarParams &p, const float *rcs, const int4 *rec, const int *range, int *pillar_at,
-                              float *heatmap, float *heatmap_feat, cudaStream_t s) {
+                              float *heatmap, float *heatmap_feat, const float *point_features, float *features,
+                              cudaStream_t s) {
   const int tiles_x = ceil_div(p.nx, 32), tiles_y = ceil_div(p.ny, 8 * R);
   float *table = nullptr;
   RCB_CUDA_TRY(cudaGetSymbolAddress((void **)&table, g_radar_tab));
   k_radar_tiles<R><<<(unsigned)(p.B * tiles_x * tiles_y), 256, 0, s>>>(p, rcs, rec, range, pillar_at, heatmap,
-                                                                      heatmap_feat, tiles_x, tiles_y, table);
+                                                                      heatmap_feat, tiles_x, tiles_y, table,
+                                                                      point_features, features);
   RCB_LAUNCH_CHECK();
   return RCB_OK;
 }
@@ -497,10 +511,14 @@ extern "C" int rcb_radar_rcs_scatter(const rcb_radar_desc *d, const float *point
     const long long base = (long long)p.B * ceil_div(p.nx, 32);
     long long budget = (long long)sms * 16;
     if (const char *e = getenv("RCB_RADAR_BUDGET")) budget = (long long)sms * atoi(e);  // development knob
-    if (base * ceil_div(p.ny, 8) <= budget) rc = launch_radar_tiles<1>(p, rcs, rec, range, pillar_at, heatmap, heatmap_feat, s);
-    else if (base * ceil_div(p.ny, 16) <= budget) rc = launch_radar_tiles<2>(p, rcs, rec, range, pillar_at, heatmap, heatmap_feat, s);
-    else if (base * ceil_div(p.ny, 32) <= budget) rc = launch_radar_tiles<4>(p, rcs, rec, range, pillar_at, heatmap, heatmap_feat, s);
-    else rc = launch_radar_tiles<8>(p, rcs, rec, range, pillar_at, heatmap, heatmap_feat, s);
+    if (base * ceil_div(p.ny, 8) <= budget) {
+      // one row per thread (small grids): the tile kernel writes the feature planes as well
+      rc = launch_radar_tiles<1>(p, rcs, rec, range, pillar_at, heatmap, heatmap_feat, point_features, features, s);
+      return rc;
+    }
+    else if (base * ceil_div(p.ny, 16) <= budget) rc = launch_radar_tiles<2>(p, rcs, rec, range, pillar_at, heatmap, heatmap_feat, nullptr, nullptr, s);
+    else if (base * ceil_div(p.ny, 32) <= budget) rc = launch_radar_tiles<4>(p, rcs, rec, range, pillar_at, heatmap, heatmap_feat, nullptr, nullptr, s);
+    else rc = launch_radar_tiles<8>(p, rcs, rec, range, pillar_at, heatmap, heatmap_feat, nullptr, nullptr, s);
     if (rc != RCB_OK) return rc;
   } else {
     int *lc = (int *)(ws + w.plane), *hb = (int *)(ws + 2 * w.plane);
