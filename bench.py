@@ -654,7 +654,7 @@ def _time_cuda(torch, fn, n_warm=3, n=10):
     return e0.elapsed_time(e1) / n
 
 
-def _pool_case(torch, rcb, rig, dev, B, grid, input_size, C, frames=1, backward=True):
+def _pool_case(torch, rcb, rig, dev, B, grid, input_size, C, frames=1, backward=True, chain=False):
     """prepare -> pool forward (-> backward) through the fused device chain on B*frames folded samples.
     Returns ms per stage, samples/s and algorithmic GB/s (SURVEY.md 8d formulas on this case's P, K, I, F, G)."""
     from rcbevdet_b200.prepare import prepare_async
@@ -692,6 +692,16 @@ def _pool_case(torch, rcb, rig, dev, B, grid, input_size, C, frames=1, backward=
                    frac_of_hbm_peak=round((alg_pf + alg_b) / (t_all * 1e-3) / 1e9 / peak, 4))
     else:
         out.update(samples_per_s=round(B / (t_fwd_all * 1e-3), 1))
+    if chain:   # the same calls in strips mode "chain" (no sort: frustum cells -> strip plan -> strip forward)
+        from rcbevdet_b200 import strips
+        old = strips.MODE
+        strips.set_mode("chain")
+        try:
+            out["chain_prepare_fwd_ms"] = round(_time_cuda(torch, lambda: rcb.voxel_pooling_v2(coor, depth, feat, lo, iv, sz)), 4)
+            if backward:
+                out["chain_prepare_fwd_bwd_ms"] = round(_time_cuda(torch, full), 4)
+        finally:
+            strips.set_mode(old)
     return out
 
 
@@ -747,7 +757,7 @@ def extra_configs(torch, rcb, rig, _lib, bp, dev, lib):
         out["temporal_8f"] = t8
         # config 5: 900x1600 -> 56x100 features, 256x256 BEV, batch sweep
         for b in (1, 2, 4, 8):
-            out[f"hires_256_B{b}"] = _pool_case(torch, rcb, rig, dev, b, rig.HIRES_GRID, rig.HIRES_INPUT, C)
+            out[f"hires_256_B{b}"] = _pool_case(torch, rcb, rig, dev, b, rig.HIRES_GRID, rig.HIRES_INPUT, C, chain=b <= 2)
             torch.cuda.empty_cache()
         out["r50_B1_latency"] = _graph_case(torch, rcb, rig, dev)
         # config 4: RCS-aware radar scatter, B=8, 5 sweeps x 5 radars x 125 points per sample

@@ -30,9 +30,10 @@ BWD_CHANNELS = (64, 80)
 #   "on"  : strip kernels for forward and backward, plan built at first use
 #   "chain": bev_pool_v2 as "off"; voxel_pooling_v2 / voxel_pooling_v2_from_calib / lss_view_transform --
 #           the chains that never hand ranks to their caller -- pool WITHOUT SORTING: frustum cells ->
-#           strip plan (it needs point_cell only) -> strip kernels, and behind them, gated on the
-#           plan's status word on the device, the sorted pipeline + cell-/pixel-stationary kernels as
-#           the fallback (no read-back: exactly one family does the work).  view_pool.py.
+#           strip plan (it needs point_cell only) -> strip forward, and behind it, gated on the plan's
+#           status word on the device, the sorted pipeline + cell-stationary forward as the fallback
+#           (no read-back: exactly one family does the work); backward on the pixel-stationary kernel
+#           (point_cell only).  view_pool.py.
 # Environment: RCB_STRIPS=off|auto|on|chain.
 MODE = os.environ.get("RCB_STRIPS", "off").lower()
 

@@ -45,7 +45,7 @@ def _oracle_grads(og, depth, feat_rows, ranks):
     (80, (1.0, 60.0, 2.0), (128, 352), 2, 3),
     (80, (1.0, 60.0, 0.5), (128, 352), 1, None),   # the R50 depth bins (D = 118)
     (64, (1.0, 60.0, 1.0), (112, 304), 2, 4),      # H = 7, W = 19: ragged strips and column groups
-    (128, (1.0, 60.0, 2.0), (112, 208), 2, None),  # backward through the (ungated) pixel kernel
+    (128, (1.0, 60.0, 2.0), (112, 208), 2, None),
     (80, (1.0, 60.0, 1.0), (288, 352), 1, 5),      # H = 18: two strips per image column
 ])
 def test_chain_against_oracle(C, depth_cfg, input_size, B, aug):
@@ -60,13 +60,14 @@ def test_chain_against_oracle(C, depth_cfg, input_size, B, aug):
     want_dg, want_fg = _oracle_grads(og, depth, feat_rows, ranks)
     _close(dg, want_dg, RTOL32, "depth_grad")
     _close(fg.permute(0, 1, 3, 4, 2), want_fg, RTOL32, "feat_grad")
-    # the strip kernels did the work (same bits as the strip kernels behind bev_pool_v2), not the fallback
+    # the strip kernels did the forward (same bits as the strip kernels behind bev_pool_v2), not the
+    # fallback; the backward is the pixel-stationary kernel's (same bits as the default chain's)
     from test_gpu_strips import _pool
     on = _pool(rcb, "on", coor, depth, feat, grid, shape, og)
     assert on[3].strips and on[3].strips.status() == 0
     assert torch.equal(bev, on[0])
-    if C != 128:
-        assert torch.equal(dg, on[1]) and torch.equal(fg, on[2])
+    off = _chain(rcb, "off", coor, depth, feat, grid, og)
+    assert torch.equal(dg, off[1]) and torch.equal(fg, off[2])
 
 
 def test_chain_falls_back_on_the_device():
