@@ -120,6 +120,17 @@ int rcb_voxel_pooling_prepare_from_calib(const rcb_prepare_desc *d, const rcb_fr
 int rcb_frustum_point_cells(const rcb_prepare_desc *d, const float *coor, const rcb_frustum_desc *fr,
                             int *point_cell, int device, rcb_stream_t stream);
 
+/* The prepare pipeline in stages: bit 1 = cells (point_cell + the bucket histograms kept in
+ * `workspace`), bit 2 = the two sort kernels (ranks_*, cell_start), bit 4 = interval_starts /
+ * interval_lengths / counts.  Same workspace across the calls of one pipeline; outputs of stages that
+ * are not requested may be NULL.  Grids up to 2^22 cells (the two-level sort); RCB_ERR_UNSUPPORTED
+ * beyond.  The sort-free chain runs stage 1 and enqueues stage 2 under a launch gate. */
+int rcb_voxel_pooling_prepare_staged(const rcb_prepare_desc *d, const float *coor, const rcb_frustum_desc *fr,
+                                     int stages, int *ranks_bev, int *ranks_depth, int *ranks_feat,
+                                     int *interval_starts, int *interval_lengths, int *point_cell, int *cell_start,
+                                     int *counts, void *workspace, size_t workspace_bytes, int device,
+                                     rcb_stream_t stream);
+
 /* Launch gate of the calling host thread (NULL clears it).  While it is set, the kernels behind
  * rcb_voxel_pooling_prepare_v2 / _from_calib, rcb_bev_pool_v2_fwd (CSR path) and rcb_bev_pool_v2_bwd
  * (structured path, its out_grad transpose included) are launched as usual but exit at once when

@@ -56,6 +56,8 @@ SIGNATURES = {
                                              [_vp] * 8 + [_vp, _sz, _i, _vp]),
     "rcb_frustum_point_cells": (_i, [ctypes.POINTER(PrepareDesc), _vp, ctypes.POINTER(FrustumDesc), _vp, _i, _vp]),
     "rcb_set_launch_gate": (_i, [_vp]),
+    "rcb_voxel_pooling_prepare_staged": (_i, [ctypes.POINTER(PrepareDesc), _vp, ctypes.POINTER(FrustumDesc), _i] +
+                                         [_vp] * 8 + [_vp, _sz, _i, _vp]),
     "rcb_debug_exactdiv_sweep": (_i, [ctypes.c_float, ctypes.POINTER(ctypes.c_ulonglong),
                                       ctypes.POINTER(ctypes.c_ulonglong), _i]),
     "rcb_pool_validate_workspace_bytes": (_sz, [ctypes.POINTER(PoolDesc)]),

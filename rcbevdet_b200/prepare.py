@@ -81,7 +81,7 @@ def pack_calib(sensor2ego, ego2global, cam2imgs, post_rots, post_trans, bda):
     return cam.contiguous(), bda.reshape(B, 9).float().contiguous()
 
 
-def _launch(desc, dev, coor=None, frustum=None, point_cell=None):
+def _launch(desc, dev, coor=None, frustum=None):
     lib = _lib.lib()
     P = desc.B * desc.N * desc.D * desc.H * desc.W
     gx, gy, gz = (int(desc.size[k]) for k in range(3))
@@ -98,7 +98,7 @@ def _launch(desc, dev, coor=None, frustum=None, point_cell=None):
     n_iv = max(1, min(P, n_cells))
     r.interval_starts = torch.empty(n_iv, **i32)
     r.interval_lengths = torch.empty(n_iv, **i32)
-    r.point_cell = torch.empty(P + 4, **i32) if point_cell is None else point_cell
+    r.point_cell = torch.empty(P + 4, **i32)
     r.cell_start = torch.empty(n_cells + 1, **i32)
     r.counts = torch.empty(4, **i32)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -147,21 +147,50 @@ def _calib_args(calib, axes, grid_lower_bound, grid_interval, grid_size, device)
 
 
 class FrustumCells:
-    """The first prepare stage alone (rcb_frustum_point_cells): point_cell, and what is needed to run
-    the rest of the pipeline on the same input later (`launch_rest`)."""
+    """The first prepare stage alone: point_cell (BEV cell of every frustum point, -1 = outside), and
+    what is needed to run the rest of the pipeline on the same input later (`launch_sort`)."""
 
-    __slots__ = ("desc", "device", "coor", "frustum", "point_cell", "grid", "B", "D", "H", "W", "HW", "P",
-                 "n_img", "n_cells")
+    __slots__ = ("desc", "device", "coor", "frustum", "point_cell", "workspace", "grid", "B", "D", "H", "W", "HW",
+                 "P", "n_img", "n_cells")
 
-    def launch_rest(self):
-        """The full pipeline on the same input (point_cell is rewritten with the same values)."""
-        return _launch(self.desc, self.device, coor=self.coor, frustum=self.frustum, point_cell=self.point_cell)
+    def _call(self, stages, r=None):
+        fd = None
+        if self.frustum is not None:
+            fd = _lib.FrustumDesc()
+            fd.u, fd.v, fd.d, fd.cam, fd.bda = (t.data_ptr() for t in self.frustum)
+        outs = [None] * 5 + [_lib.ptr(self.point_cell), None, None]
+        if r is not None:
+            outs = [_lib.ptr(r.ranks_bev), _lib.ptr(r.ranks_depth), _lib.ptr(r.ranks_feat), None, None,
+                    _lib.ptr(self.point_cell), _lib.ptr(r.cell_start), None]
+        _lib.check(_lib.lib().rcb_voxel_pooling_prepare_staged(
+            ctypes.byref(self.desc), _lib.ptr(self.coor), ctypes.byref(fd) if fd is not None else None, stages, *outs,
+            _lib.ptr(self.workspace), self.workspace.numel(), self.device.index, _lib.stream_ptr(self.device)),
+            "rcb_voxel_pooling_prepare_staged")
+
+    def launch_sort(self):
+        """Stage 2 (the two sort kernels) on the histograms stage 1 left in the workspace: ranks and the
+        dense CSR, no interval arrays (the cell-stationary forward reads the CSR)."""
+        i32 = dict(dtype=torch.int32, device=self.device)
+        r = PreparedRanks()
+        r.ranks_bev, r.ranks_depth, r.ranks_feat = (torch.empty(self.P, **i32) for _ in range(3))
+        r.cell_start = torch.empty(self.n_cells + 1, **i32)
+        r.point_cell, r.interval_starts, r.interval_lengths, r.counts = self.point_cell, None, None, None
+        r.grid, r.B, r.D, r.HW, r.H, r.P, r.n_cells = self.grid, self.B, self.D, self.HW, self.H, self.P, self.n_cells
+        self._call(2, r)
+        return r
+
+
+def staged_supported(B, cells_per_sample):
+    """The staged pipeline (and the launch gate) exist for the two-level sort only: <= 1024 buckets of
+    <= 2^12 cells."""
+    return B * -(-cells_per_sample // 4096) <= 1024
 
 
 def point_cells_async(coor=None, calib=None, axes=None, grid_lower_bound=None, grid_interval=None, grid_size=None,
                       device=None):
-    """BEV cell of every frustum point (-1 = outside), from `coor` or from the calibration; no sort,
-    no read-back."""
+    """Stage 1 of the prepare pipeline: BEV cell of every frustum point, from `coor` or from the
+    calibration; no sort, no read-back.  None when the geometry is outside the staged pipeline's
+    envelope."""
     r = FrustumCells()
     if coor is not None:
         r.desc, r.coor = _coor_args(coor, grid_lower_bound, grid_interval, grid_size)
@@ -171,17 +200,17 @@ def point_cells_async(coor=None, calib=None, axes=None, grid_lower_bound=None, g
         r.coor = None
     d = r.desc
     gx, gy, gz = (int(d.size[k]) for k in range(3))
+    if not staged_supported(d.B, gx * gy * gz):
+        return None
+    ws_bytes = _lib.lib().rcb_prepare_workspace_bytes(ctypes.byref(d))
+    if ws_bytes == 0:
+        return None
     r.grid = (gz, gy, gx)
     r.B, r.D, r.H, r.W, r.HW, r.n_img = d.B, d.D, d.H, d.W, d.H * d.W, d.B * d.N
     r.P, r.n_cells = d.B * d.N * d.D * d.H * d.W, d.B * gx * gy * gz
     r.point_cell = torch.empty(r.P + 4, dtype=torch.int32, device=r.device)
-    fd = None
-    if r.frustum is not None:
-        fd = _lib.FrustumDesc()
-        fd.u, fd.v, fd.d, fd.cam, fd.bda = (t.data_ptr() for t in r.frustum)
-    _lib.check(_lib.lib().rcb_frustum_point_cells(ctypes.byref(d), _lib.ptr(r.coor), ctypes.byref(fd) if fd is not None else None,
-                                                  _lib.ptr(r.point_cell), r.device.index, _lib.stream_ptr(r.device)),
-               "rcb_frustum_point_cells")
+    r.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=r.device)
+    r._call(1)
     return r
 
 

@@ -87,7 +87,7 @@ class _ChainPool(torch.autograd.Function):
         out = torch.empty(shape, dtype=torch.float32, device=dev)
         _strips.forward(sp, d, depth_c, rows, out)
         with _lib.launch_gate(sp.status_tensor()):
-            prepared = cells.launch_rest()
+            prepared = cells.launch_sort()
             _bp.pool_forward(d, depth_c, rows, prepared.ranks_depth, prepared.ranks_feat, prepared.ranks_bev, None,
                              None, prepared.cell_start, out)
         ctx.save_for_backward(depth_c, rows, cells.point_cell)
@@ -126,12 +126,7 @@ class _ChainPool(torch.autograd.Function):
 def _chain(cells, C, depth, feat, channels_last):
     """The sort-free chain when it applies (mode, channel count, geometry), else None.  `feat` is the
     (B, N, H, W, C) view the pooling operators take (view_transformer.py:195)."""
-    if _strips.MODE != "chain" or C not in _strips.FWD_CHANNELS:
-        return None
-    # the gated fallback needs the two-level sort (its kernels take the launch gate): <= 1024 buckets of
-    # <= 2^12 cells
-    cps = cells.n_cells // max(cells.B, 1)
-    if cells.B * -(-cps // 4096) > 1024:
+    if cells is None or _strips.MODE != "chain" or C not in _strips.FWD_CHANNELS:
         return None
     sp = _strips.build(cells.point_cell, None, cells.n_img, cells.D, cells.H, cells.W, cells.n_cells)
     if sp is None:

@@ -217,3 +217,37 @@ def test_lss_view_transform_takes_the_chain():
     for a, b, what in zip(res["chain"], res["off"], ("bev", "grad")):
         assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()), what
     assert not torch.equal(res["chain"][0], res["off"][0])   # another summation order: the strip kernels ran
+
+
+def test_point_cells_and_staged_prepare_entries():
+    """rcb_frustum_point_cells == the point_cell of the full pipeline; rcb_voxel_pooling_prepare_staged
+    (stage 1, then stages 2 | 4) == the one-call pipeline, bit for bit."""
+    import rcbevdet_b200 as rcb
+    from rcbevdet_b200 import _lib, rig
+    from rcbevdet_b200.prepare import _coor_args, prepare_async
+    coor, _, _ = _case(B=2, aug=3)
+    lo, iv, sz = rig.grid_tensors(rig.R50_GRID)
+    ref = prepare_async(coor.cuda(), lo, iv, sz)
+    desc, c = _coor_args(coor.cuda(), lo, iv, sz)
+    lib = _lib.lib()
+    P = coor.numel() // 3
+    pc = torch.full((P + 4,), -7, dtype=torch.int32, device="cuda")
+    _lib.check(lib.rcb_frustum_point_cells(ctypes.byref(desc), _lib.ptr(c), None, _lib.ptr(pc), 0, None), "point_cells")
+    assert torch.equal(pc[:P], ref.point_cell[:P])
+    ws = torch.empty(lib.rcb_prepare_workspace_bytes(ctypes.byref(desc)), dtype=torch.uint8, device="cuda")
+    i32 = dict(dtype=torch.int32, device="cuda")
+    rb, rd, rf = (torch.empty(P, **i32) for _ in range(3))
+    n_cells = ref.n_cells
+    st, ln = torch.empty(n_cells, **i32), torch.empty(n_cells, **i32)
+    cs, counts, pc2 = torch.empty(n_cells + 1, **i32), torch.empty(4, **i32), torch.empty(P + 4, **i32)
+    tail = (_lib.ptr(ws), ws.numel(), 0, None)
+    _lib.check(lib.rcb_voxel_pooling_prepare_staged(ctypes.byref(desc), _lib.ptr(c), None, 1, None, None, None, None, None,
+                                                    _lib.ptr(pc2), None, None, *tail), "stage 1")
+    _lib.check(lib.rcb_voxel_pooling_prepare_staged(ctypes.byref(desc), None, None, 6, _lib.ptr(rb), _lib.ptr(rd),
+                                                    _lib.ptr(rf), _lib.ptr(st), _lib.ptr(ln), _lib.ptr(pc2), _lib.ptr(cs),
+                                                    _lib.ptr(counts), *tail), "stages 2 | 4")
+    k, n_iv = (int(v) for v in counts[:2].tolist())
+    assert [k, n_iv] == ref.counts[:2].tolist()
+    for a, b in ((rb[:k], ref.ranks_bev[:k]), (rd[:k], ref.ranks_depth[:k]), (rf[:k], ref.ranks_feat[:k]),
+                 (st[:n_iv], ref.interval_starts[:n_iv]), (ln[:n_iv], ref.interval_lengths[:n_iv]), (cs, ref.cell_start)):
+        assert torch.equal(a, b)
