@@ -50,7 +50,10 @@ __global__ void __launch_bounds__(256) k_planes_to_rows(const TIn *__restrict__ 
 // 256 contiguous bytes; stores: the 64*C output floats are ONE contiguous run.  The generic kernel
 // above spends ~36 instructions per element on index arithmetic and is issue-bound (ncu: 75 %
 // issue-active at 3.2 TB/s); this one moves four elements per load/store instruction.
-constexpr int kV4Pixels = 64;
+#ifndef RCB_V4_PIXELS
+#define RCB_V4_PIXELS 64
+#endif
+constexpr int kV4Pixels = RCB_V4_PIXELS;
 #ifndef RCB_V4_MIN_HW
 #define RCB_V4_MIN_HW 256
 #endif
