@@ -251,3 +251,23 @@ def test_point_cells_and_staged_prepare_entries():
     for a, b in ((rb[:k], ref.ranks_bev[:k]), (rd[:k], ref.ranks_depth[:k]), (rf[:k], ref.ranks_feat[:k]),
                  (st[:n_iv], ref.interval_starts[:n_iv]), (ln[:n_iv], ref.interval_lengths[:n_iv]), (cs, ref.cell_start)):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("aug", [None, 3])
+def test_chain_hires_against_default(aug):
+    """BASELINE config 5's geometry (900 x 1600 -> 56 x 100 features, 256^2 BEV), one sample: the sort-free
+    chain against the default chain, rel 1e-5.  Without augmentation the strip plan holds (the bits
+    differ from the cell kernel's); with it the plan may refuse and the gated fallback answers."""
+    import rcbevdet_b200 as rcb
+    from rcbevdet_b200 import rig
+    grid = rig.HIRES_GRID
+    coor = rig.lidar_coor(rig.camera_rig(1, input_size=rig.HIRES_INPUT, aug_seed=aug), grid["depth"], rig.HIRES_INPUT, 16)
+    _, N, D, H, W, _ = coor.shape
+    depth, feat = rig.pooling_inputs(1, N, D, H, W, 80, seed=6)
+    og = torch.randn((1, 80, 1, 256, 256), generator=torch.Generator().manual_seed(4))
+    ref = _chain(rcb, "off", coor, depth, feat, grid, og)
+    got = _chain(rcb, "chain", coor, depth, feat, grid, og)
+    for name, x, y in zip(("bev", "depth_grad", "feat_grad"), got, ref):
+        _close(x, y.cpu().numpy(), RTOL32, name)
+    if aug is None:
+        assert not torch.equal(got[0], ref[0]), "the strip kernels should have pooled this one"
