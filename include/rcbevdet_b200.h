@@ -132,7 +132,7 @@ int rcb_voxel_pooling_prepare_staged(const rcb_prepare_desc *d, const float *coo
                                      rcb_stream_t stream);
 
 /* Launch gate of the calling host thread (NULL clears it).  While it is set, the kernels behind
- * rcb_voxel_pooling_prepare_v2 / _from_calib, rcb_bev_pool_v2_fwd (CSR path) and rcb_bev_pool_v2_bwd
+ * rcb_voxel_pooling_prepare_v2 / _from_calib / _staged, rcb_bev_pool_v2_fwd (CSR path) and rcb_bev_pool_v2_bwd
  * (structured path, its out_grad transpose included) are launched as usual but exit at once when
  * *gate == 0 on the device; entry points that would take a kernel without a gate return
  * RCB_ERR_UNSUPPORTED.  With gate = the status word of a strip plan this enqueues the general
