@@ -23,6 +23,8 @@
 //
 // The patch leaves through a shared-memory transpose as (B, C, Z*Y*X) runs of kPatchX cells per
 // channel row, or directly as channels-last rows.  Empty cells get their zeros here.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rcb {
@@ -54,6 +56,22 @@ constexpr int kFwdRounds = kPatchCells / kFwdWarps;    // cells per warp
 constexpr int kTilePitch = kPatchCells + 1;
 constexpr int kRowsInFlight = RCB_FWD_ROWS;
 static_assert(kPatchCells % 32 == 0 && kPatchCells % kFwdWarps == 0 && kCellWarps <= kFwdWarps, "patch shape");
+
+// CTA shapes.  The kernel's duration is bounded from below by its heaviest patch (the patches next to
+// the cameras hold tens of times the mean), which its CTA works off with `warps` warps and `rows`
+// context rows in flight per warp.  With many samples in the launch the SMs stay full while those
+// patches run and the densest packing wins (shape 0: 40 warps per SM); with few samples the heavy
+// patches ARE the kernel and a CTA that throws more warps and more loads at its patch wins, although
+// fewer CTAs fit an SM.  Measured forward (us), R50 grid B = 1 / 2 / 4 / 8 and 900x1600 / 256^2 grid
+// B = 1 / 2 / 4:   shape 0: 48 / 52 / 60 / 76 and 238 / 249 / 288
+//                  shape 1: 29 / 35 / 51 / 97 and 145 / 154 / 288
+//                  shape 2: 22 / 38 / 74 / 144 and 116 / 204 / 418
+// Every shape pools a cell with one warp in point order: the results are bit-identical.
+template <int kShape> struct FwdShape;
+template <> struct FwdShape<0> { static constexpr int warps = kFwdWarps, rows = kRowsInFlight, ctas = RCB_FWD_CTAS; };
+template <> struct FwdShape<1> { static constexpr int warps = 16, rows = 4, ctas = 2; };   // 64 registers
+template <> struct FwdShape<2> { static constexpr int warps = 16, rows = 8, ctas = 1; };   // 124 registers
+static_assert(kPatchCells % 16 == 0, "patch shape");
 static_assert((kPatchX & (kPatchX - 1)) == 0, "kPatchX is a power of two");
 
 struct FwdCellsParams {
@@ -102,10 +120,13 @@ struct FwdChunk {
 
 // kQ channel quads per lane (quad j of lane l = l + j * lanes); kLanes lanes carry a row
 // (C = 4 * kQ * lanes), kLanes == 0: run time.
-template <typename FeatT, int kLanes, int kQ>
-__global__ void __launch_bounds__(32 * kFwdWarps, RCB_FWD_CTAS) k_fwd_cells(FwdCellsParams p) {
+template <typename FeatT, int kLanes, int kQ, int kShape>
+__global__ void __launch_bounds__(32 * FwdShape<kShape>::warps, FwdShape<kShape>::ctas) k_fwd_cells(FwdCellsParams p) {
   pdl_prologue();
   if (gate_closed(p.gate)) return;
+  constexpr int kFwdWarps = FwdShape<kShape>::warps;        // (shadow the namespace-scope defaults)
+  constexpr int kRowsInFlight = FwdShape<kShape>::rows;
+  constexpr int kFwdRounds = kPatchCells / kFwdWarps;
   extern __shared__ __align__(16) float cells_ts[];  // [C][kTilePitch] write-out tile (B_C_CELLS layout only)
   __shared__ __align__(16) uint2 s_ent[kFwdWarps][32];
   __shared__ int s_lo[kPatchCells], s_hi[kPatchCells];
@@ -360,17 +381,36 @@ __global__ void __launch_bounds__(32 * kFwdWarps, RCB_FWD_CTAS) k_fwd_cells(FwdC
   }
 }
 
-template <typename FeatT, int kLanes, int kQ>
-static int launch_cells_t(const FwdCellsParams &p, long long grid, cudaStream_t s) {
+template <typename FeatT, int kLanes, int kQ, int kShape>
+static int launch_cells_s(const FwdCellsParams &p, long long grid, cudaStream_t s) {
   const size_t smem = p.layout == RCB_LAYOUT_B_C_CELLS ? align_up((size_t)p.C * kTilePitch * 4, 16) : 0;
   if (smem > 40 * 1024)
-    RCB_CUDA_TRY(cudaFuncSetAttribute(k_fwd_cells<FeatT, kLanes, kQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RCB_CUDA_TRY(cudaFuncSetAttribute(k_fwd_cells<FeatT, kLanes, kQ, kShape>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // the kernel lives on L1-resident context rows: prefer a small shared-memory partition (measured
   // on the R50 workload: 29 % -> L1 hit rate 45 -> 49 %, 78.4 -> 76.7 us; the driver rounds up to
   // what the resident CTAs need)
-  RCB_CUDA_TRY(cudaFuncSetAttribute(k_fwd_cells<FeatT, kLanes, kQ>, cudaFuncAttributePreferredSharedMemoryCarveout, RCB_FWD_CARVEOUT));
-  RCB_CUDA_TRY(launch_pdl(k_fwd_cells<FeatT, kLanes, kQ>, (unsigned)grid, 32 * kFwdWarps, smem, s, p));
+  RCB_CUDA_TRY(cudaFuncSetAttribute(k_fwd_cells<FeatT, kLanes, kQ, kShape>, cudaFuncAttributePreferredSharedMemoryCarveout, RCB_FWD_CARVEOUT));
+  RCB_CUDA_TRY(launch_pdl(k_fwd_cells<FeatT, kLanes, kQ, kShape>, (unsigned)grid, 32 * FwdShape<kShape>::warps, smem, s, p));
   return RCB_OK;
+}
+
+// few samples: the heavy patches bound the kernel (see FwdShape); RCB_FWD_SHAPE=0|1|2 overrides
+static int fwd_shape_for(int B) {
+  static const int forced = [] {
+    const char *e = getenv("RCB_FWD_SHAPE");
+    return e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : -1;
+  }();
+  if (forced >= 0) return forced;
+  return B <= 1 ? 2 : (B <= 4 ? 1 : 0);
+}
+
+template <typename FeatT, int kLanes, int kQ>
+static int launch_cells_t(const FwdCellsParams &p, long long grid, cudaStream_t s) {
+  switch (fwd_shape_for(p.B)) {
+    case 2: return launch_cells_s<FeatT, kLanes, kQ, 2>(p, grid, s);
+    case 1: return launch_cells_s<FeatT, kLanes, kQ, 1>(p, grid, s);
+    default: return launch_cells_s<FeatT, kLanes, kQ, 0>(p, grid, s);
+  }
 }
 
 template <typename FeatT>

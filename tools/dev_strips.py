@@ -95,6 +95,9 @@ if __name__ == "__main__":
         aug = int(sys.argv[3]) if len(sys.argv) > 3 else None
         ok = run(B, rig.R50_GRID, rig.R50_INPUT, rig.R50_GRID["depth"], aug=aug, time=True)
         sys.exit(0 if ok or os.environ.get("RCB_DEV_NOCHECK") else 1)
+    if len(sys.argv) > 2 and sys.argv[2] == "hires":    # the 900 x 1600 / 256^2 case only, B samples
+        ok = run(B, rig.HIRES_GRID, rig.HIRES_INPUT, rig.HIRES_GRID["depth"], time=True)
+        sys.exit(0 if ok or os.environ.get("RCB_DEV_NOCHECK") else 1)
     ok = True
     ok &= run(1, rig.R50_GRID, (64, 176), (1.0, 60.0, 4.0))
     ok &= run(2, rig.R50_GRID, (128, 352), (1.0, 60.0, 2.0), aug=3)
