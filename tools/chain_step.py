@@ -13,7 +13,7 @@ mode = sys.argv[1] if len(sys.argv) > 1 else "chain"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 from_calib = len(sys.argv) > 3 and sys.argv[3] == "calib"
 strips.set_mode(mode)
-B, C = 8, 80
+B, C = int(os.environ.get("RCB_B", "8")), 80
 grid = rig.R50_GRID
 calib = rig.camera_rig(B, aug_seed=3)
 coor = rig.lidar_coor(calib, grid["depth"], rig.R50_INPUT, 16).cuda()
