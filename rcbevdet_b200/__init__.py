@@ -9,6 +9,7 @@ Public surface (mirrors the reference's names):
     radar_rcs_scatter, PointPillarsScatterRCS       <- mmdet3d/models/middle_encoders/pillar_scatter.py
     depth_context_split, lss_view_transform         <- LSSViewTransformer.forward's split + softmax (view_transformer.py:316-320)
     shift_feature, gen_grid_transform               <- BEVDepth4D.shift_feature / gen_grid (bevdet_rc.py:585-657)
+    GraphedViewPool                                 <- voxel_pooling_v2_from_calib replayed from a CUDA graph (inference)
 Everything computes in librcbevdet_b200.so (hand-written CUDA behind a C ABI, include/
 rcbevdet_b200.h); importing this package does not need a GPU, calling an operator does.
 """
@@ -19,6 +20,7 @@ from .view_pool import voxel_pooling_v2, voxel_pooling_v2_from_calib  # noqa: F4
 from .radar import PointPillarsScatterRCS, radar_rcs_scatter  # noqa: F401
 from .temporal import gen_grid_transform, shift_feature  # noqa: F401
 from .lift import depth_context_split, lss_view_transform  # noqa: F401
-from . import strips  # noqa: F401  (strip kernels: strips.set_mode("auto" | "on" | "off"))
+from .graphed import GraphedViewPool  # noqa: F401
+from . import strips  # noqa: F401  (strip kernels: strips.set_mode("auto" | "on" | "off" | "chain"))
 
 __version__ = "0.1.0"

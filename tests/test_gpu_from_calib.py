@@ -227,3 +227,24 @@ def test_fused_chains_with_nothing_inside_the_grid():
     x = torch.randn(B * 6, D + C, H, W, device="cuda")
     bev, dep = rcb.lss_view_transform(x, 6, D, C, tuple(far), axes, lo, iv, sz)
     assert float(bev.abs().max()) == 0.0 and dep.shape == (B * 6, D, H, W)
+
+
+def test_graphed_view_pool_replays_with_new_inputs():
+    """GraphedViewPool: captured once per input signature, replayed with new depth / context / calibration;
+    bit-identical to the eager chain."""
+    import rcbevdet_b200 as rcb
+    from rcbevdet_b200 import rig
+    lo, iv, sz = rig.grid_tensors(rig.R50_GRID)
+    axes = rcb.frustum_axes(rig.R50_GRID["depth"], rig.R50_INPUT, 16, device="cuda")
+    pool = rcb.GraphedViewPool(axes, lo, iv, sz)
+    for seed, aug in ((1, None), (5, 3), (7, 4)):
+        calib = rig.camera_rig(1, aug_seed=aug)
+        depth, feat = (t.cuda() for t in rig.pooling_inputs(1, 6, 118, 16, 44, 80, seed=seed))
+        got = pool(calib, depth, feat).clone()
+        want = rcb.voxel_pooling_v2_from_calib(calib, axes, depth, feat, lo, iv, sz)
+        assert torch.equal(got, want)
+    assert len(pool._graphs) == 1
+    depth2, feat2 = (t.cuda() for t in rig.pooling_inputs(2, 6, 118, 16, 44, 80, seed=2))   # another signature
+    got = pool(rig.camera_rig(2), depth2, feat2)
+    assert torch.equal(got, rcb.voxel_pooling_v2_from_calib(rig.camera_rig(2), axes, depth2, feat2, lo, iv, sz))
+    assert len(pool._graphs) == 2
