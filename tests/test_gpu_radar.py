@@ -160,3 +160,38 @@ def test_tile_and_splat_forms_agree(monkeypatch):
     b = rcb.radar_rcs_scatter(pf, rc, co, 2, 128, 128)
     assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
     assert _ulp_close(a[1].cpu().numpy(), b[1].cpu().numpy())
+
+
+@pytest.mark.parametrize("ny,nx,B", [(100, 176, 3), (33, 41, 2), (8, 1000, 1), (300, 20, 2)])
+def test_tile_form_writes_inside_its_buffers(ny, nx, B):
+    """Guard bands around every output and the workspace of the C-ABI call (ragged tiles, grids narrower
+    than a tile, several rows per thread): nothing outside the declared extents is written."""
+    import ctypes
+    from rcbevdet_b200 import _lib
+    from rcbevdet_b200.radar import _desc
+    pf, rc, co = _edge_case(3, B, ny, nx, min(40, ny * nx // 4), 40.0, cin=8)
+    pf, rc, co = pf.cuda(), rc.cuda(), co.cuda()
+    d = _desc(pf, rc, B, ny, nx)
+    lib = _lib.lib()
+    G = 1024                                                # guard elements on each side (16-byte aligned)
+
+    def guarded(n, dtype=torch.float32):
+        t = torch.full((n + 2 * G,), -123.0 if dtype == torch.float32 else 77, dtype=dtype, device="cuda")
+        return t, t[G:G + n]
+
+    cells = B * ny * nx
+    fa, f = guarded(cells * 8)
+    ha, h = guarded(cells)
+    hfa, hf = guarded(cells)
+    ws_bytes = lib.rcb_radar_workspace_bytes(ctypes.byref(d))
+    wa, ws = guarded(ws_bytes, torch.uint8)
+    _lib.check(lib.rcb_radar_rcs_scatter(ctypes.byref(d), _lib.ptr(pf), _lib.ptr(rc), _lib.ptr(co), _lib.ptr(f), _lib.ptr(h),
+                                         _lib.ptr(hf), _lib.ptr(ws), ws_bytes, 0, None), "radar")
+    torch.cuda.synchronize()
+    for name, full, n in (("features", fa, cells * 8), ("heatmap", ha, cells), ("heatmap_feat", hfa, cells)):
+        assert float((full[:G] + 123.0).abs().max()) == 0.0 and float((full[G + n:] + 123.0).abs().max()) == 0.0, name
+    assert int((wa[:G] != 77).sum()) == 0 and int((wa[G + ws_bytes:] != 77).sum()) == 0, "workspace"
+    wf, wh, whf = oracle.radar_rcs_scatter(pf.cpu().numpy(), rc.cpu().numpy(), co.cpu().numpy(), B, ny, nx)
+    assert np.array_equal(f.view(B, 8, ny, nx).cpu().numpy(), wf)
+    assert np.array_equal(hf.view(B, 1, ny, nx).cpu().numpy(), whf)
+    assert _ulp_close(h.view(B, ny, nx).cpu().numpy(), wh)

@@ -203,3 +203,45 @@ def test_c_abi_refuses_what_it_cannot_do():
     rc = lib.rcb_bev_pool_v2_fwd_strips(ctypes.byref(d), ctypes.byref(sd), _lib.ptr(x), _lib.ptr(x), _lib.ptr(x),
                                         _lib.ptr(x), _lib.ptr(x), 64, 0, None)
     assert rc == -3   # RCB_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("input_size,depth_cfg,B,aug", [((112, 304), (1.0, 60.0, 1.0), 2, 4), ((288, 352), (1.0, 60.0, 2.0), 1, 5)])
+def test_plan_and_rows_stay_inside_their_buffers(input_size, depth_cfg, B, aug):
+    """Guard bands around the plan buffer and the segment-row scratch of the C-ABI calls (ragged strips
+    and column groups): the plan kernels (k_strip_plan, k_seg_prefix / _fill / _assign) and the strip
+    forward write nothing outside the extents rcb_strip_plan_bytes / rcb_strip_rows_bytes declare."""
+    import rcbevdet_b200 as rcb
+    from rcbevdet_b200 import _lib, bev_pool as bp, rig
+    from rcbevdet_b200.prepare import prepare_async
+    grid = rig.R50_GRID
+    coor, depth, feat = _case(B=B, depth_cfg=depth_cfg, input_size=input_size, C=80, aug=aug, seed=3)
+    lo, iv, sz = rig.grid_tensors(grid)
+    r = prepare_async(coor.cuda(), lo, iv, sz)
+    _, N, D, H, W, _ = coor.shape
+    sd = _lib.StripDesc()
+    sd.n_img, sd.D, sd.H, sd.W, sd.n_cells = B * N, D, H, W, r.n_cells
+    lib = _lib.lib()
+    G = 4096
+    n_plan = lib.rcb_strip_plan_bytes(ctypes.byref(sd))
+    n_rows = lib.rcb_strip_rows_bytes(ctypes.byref(sd), 80)
+    plan_all = torch.full((n_plan + 2 * G,), 0x5a, dtype=torch.uint8, device="cuda")
+    rows_all = torch.full((n_rows + 2 * G,), 0x5a, dtype=torch.uint8, device="cuda")
+    plan, rows_ws = plan_all[G:G + n_plan], rows_all[G:G + n_rows]
+    _lib.check(lib.rcb_strip_plan_build(ctypes.byref(sd), _lib.ptr(r.point_cell), None, _lib.ptr(plan), n_plan, 0, None), "plan")
+    assert int(plan[:4].view(torch.int32).item()) == 0
+    dc = depth.cuda()
+    frows = feat.permute(0, 1, 3, 4, 2).contiguous().view(-1, 80).cuda()
+    d = _lib.PoolDesc()
+    d.n_points, d.n_intervals, d.C = r.P, 0, 80
+    d.B, d.Z, d.Y, d.X = B, 1, 128, 128
+    d.n_depth, d.n_pixels, d.D, d.HW, d.H = dc.numel(), frows.shape[0], D, H * W, H
+    d.layout, d.feat_dtype, d.flags = _lib.LAYOUT_B_C_CELLS, _lib.DTYPE_F32, _lib.PLAN_ALL
+    out = torch.empty((B, 80, 1, 128, 128), device="cuda")
+    _lib.check(lib.rcb_bev_pool_v2_fwd_strips(ctypes.byref(d), ctypes.byref(sd), _lib.ptr(plan), _lib.ptr(dc), _lib.ptr(frows),
+                                              _lib.ptr(out), _lib.ptr(rows_ws), n_rows, 0, None), "fwd_strips")
+    torch.cuda.synchronize()
+    for name, full, n in (("plan", plan_all, n_plan), ("rows", rows_all, n_rows)):
+        assert int((full[:G] != 0x5a).sum()) == 0 and int((full[G + n:] != 0x5a).sum()) == 0, name
+    ref = torch.empty_like(out)
+    bp.pool_forward(d, dc, frows, r.ranks_depth, r.ranks_feat, r.ranks_bev, None, None, r.cell_start, ref)
+    _close(out, ref.cpu().numpy(), RTOL32, "strip forward through the guarded buffers")
