@@ -85,23 +85,26 @@ def test_strips_channels_last_bf16_and_reproducible():
 
 def test_auto_mode_switches_on_reuse():
     """Cached ranks (the reference's accelerate mode): the second forward on the same ranks builds the
-    strip plan and runs the strip kernels; the first one does not pay for a plan."""
+    strip plan and runs the strip kernels; the first one does not pay for a plan.  One or two samples on
+    a small grid stay on the cell-stationary kernel (its small-batch CTA shapes are as fast there)."""
     import rcbevdet_b200 as rcb
     from rcbevdet_b200 import rig, strips, plan as _plan
     strips.set_mode("auto")
     grid = rig.R50_GRID
-    coor, depth, feat = _case(B=1, depth_cfg=(1.0, 60.0, 0.5), input_size=(128, 352))
-    ranks, shape, feat_rows, want = _oracle_pool(coor, depth, feat, grid)
-    lo, iv, sz = rig.grid_tensors(grid)
-    rb, rd, rf, st, ln = rcb.voxel_pooling_prepare_v2(coor.cuda(), lo, iv, sz)
-    plan = _plan.lookup(rd, rf, rb, st, ln, shape[0] * shape[1] * shape[2] * shape[3], depth.numel())
-    with torch.no_grad():
-        first = rcb.bev_pool_v2(depth.cuda(), feat.cuda().permute(0, 1, 3, 4, 2), rd, rf, rb, shape, st, ln)
-        assert plan.strips is None
-        second = rcb.bev_pool_v2(depth.cuda(), feat.cuda().permute(0, 1, 3, 4, 2), rd, rf, rb, shape, st, ln)
-        assert isinstance(plan.strips, strips.StripPlan)
-    _close(first, oracle.to_bczyx(want), RTOL32, "cells kernel")
-    _close(second, oracle.to_bczyx(want), RTOL32, "strip kernels")
+    for B, switches in ((3, True), (1, False)):
+        coor, depth, feat = _case(B=B, depth_cfg=(1.0, 60.0, 0.5), input_size=(128, 352))
+        ranks, shape, feat_rows, want = _oracle_pool(coor, depth, feat, grid)
+        lo, iv, sz = rig.grid_tensors(grid)
+        rb, rd, rf, st, ln = rcb.voxel_pooling_prepare_v2(coor.cuda(), lo, iv, sz)
+        plan = _plan.lookup(rd, rf, rb, st, ln, shape[0] * shape[1] * shape[2] * shape[3], depth.numel())
+        with torch.no_grad():
+            first = rcb.bev_pool_v2(depth.cuda(), feat.cuda().permute(0, 1, 3, 4, 2), rd, rf, rb, shape, st, ln)
+            assert plan.strips is None
+            second = rcb.bev_pool_v2(depth.cuda(), feat.cuda().permute(0, 1, 3, 4, 2), rd, rf, rb, shape, st, ln)
+            assert isinstance(plan.strips, strips.StripPlan) == switches
+        _close(first, oracle.to_bczyx(want), RTOL32, "cells kernel")
+        _close(second, oracle.to_bczyx(want), RTOL32, "second call")
+        assert torch.equal(first, second) != switches
 
 
 def test_foreign_int64_ranks_take_the_strip_kernels_too():
