@@ -55,7 +55,8 @@ constexpr int kTabR = 64;  // tabulated radii / offsets: G[r][|dy|][|dx|], r, |d
 // value is never zero (its minimum, at the corners, is exp(-36 r^2 / (2r+1)^2) > exp(-9)), so
 // "value > 0" IS the window test: the hot loop needs no comparison against the radius.  1 MB, L2
 // resident, the part within reach of the common radii L1 resident.
-constexpr int kTabStride = kTabR * kTabR + 1;  // per radius: the 64 x 64 offsets + one zero that out-of-table offsets clamp to
+constexpr int kTabW = 128;                       // offsets per table row / rows per radius: every offset a tile can see
+constexpr int kTabStride = kTabW * kTabW;        // (|dx| <= r + 31, |dy| <= r + 8 R - 1 <= 126 for r < 64) has an entry, zero outside the window
 __device__ float g_radar_tab[kTabR * kTabStride];
 
 __device__ __forceinline__ double radar_denom(int radius) {
@@ -82,7 +83,7 @@ __device__ __noinline__ float radar_value_big(int ax, int ay, int radius) {
 __global__ void __launch_bounds__(256) k_radar_table() {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kTabR * kTabStride) return;
-  const int r = i / kTabStride, o = i % kTabStride, ay = o / kTabR, ax = o % kTabR;
+  const int r = i / kTabStride, o = i % kTabStride, ay = o / kTabW, ax = o % kTabW;
   const double denom = radar_denom(r);
   g_radar_tab[i] = (ax > r || ay > r) ? 0.f : radar_value(radar_factor(ax, denom), radar_factor(ay, denom));  // o == 4096: ay = 64 > r
 }
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(256) k_radar_tiles(RadarParams p, const float 
                                                      const float *__restrict__ table,
                                                      const float *__restrict__ point_features,
                                                      float *__restrict__ features) {
+  pdl_prologue();  // launched with programmatic stream serialisation behind k_radar_records
   __shared__ int4 s_list[kScanChunk];
   __shared__ int s_own[R * 256];  // pillar at each cell of the tile (index + 1), thread-major like the registers
   __shared__ int s_n, s_nbig;
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(256) k_radar_tiles(RadarParams p, const float 
   const int x1 = min(x0 + 31, p.nx - 1), y1 = min(y0 + 8 * R - 1, p.ny - 1);
   const int v_lo = p.V - range[2 * b], v_hi = range[2 * b + 1];  // empty sample: v_lo = V, v_hi = 0
   const int cx = x0 + lane, cy = y0 + warp;                      // cell j of the thread: (cx, cy + 8j)
-  const int cy64 = cy << 6;
+  const int cy64 = cy * kTabW;   // (row offsets are pre-scaled by the table's row pitch)
   float best[R];
   int last[R];
 #pragma unroll
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(256) k_radar_tiles(RadarParams p, const float 
       if (q[k].w == b && q[k].z >= 0 && abs(ddx) <= q[k].z && abs(ddy) <= q[k].z) {
         const int v1 = v0 + k * 256 + tid + 1;
         // small radii fill the list from the front, radii beyond the table from the back
-        if (q[k].z < kTabR) s_list[atomicAdd(&s_n, 1)] = make_int4(q[k].x, q[k].y << 6, q[k].z * kTabStride, v1);
+        if (q[k].z < kTabR) s_list[atomicAdd(&s_n, 1)] = make_int4(q[k].x, q[k].y * kTabW, q[k].z * kTabStride, v1);
         else s_list[kScanChunk - 1 - atomicAdd(&s_nbig, 1)] = make_int4(q[k].x, q[k].y, q[k].z, v1);
         if ((ddx | ddy) == 0) {  // the pillar's own cell is in this tile
           const int ly = q[k].y - y0;
@@ -168,15 +170,13 @@ __global__ void __launch_bounds__(256) k_radar_tiles(RadarParams p, const float 
     __syncthreads();
     const int n = s_n;
     for (int i = 0; i < n; ++i) {
-      const int4 e = s_list[i];                      // x, y << 6, radius * kTabStride, index + 1
-      const unsigned ax = __sad(cx, e.x, 0u);        // |dx|
+      const int4 e = s_list[i];                      // x, y * kTabW, radius * kTabStride, index + 1
+      const unsigned ax = __sad(cx, e.x, (unsigned)e.z);   // |dx| + the radius' table base
 #pragma unroll
       for (int j = 0; j < R; ++j) {
-        const unsigned off = __sad(cy64 + 512 * j, e.y, ax);   // |dy| * 64 + |dx|
-        // offsets outside the table (|dx| or |dy| >= 64) read the radius' zero entry: no branch, the loads
-        // of an unrolled trip stay in flight together
-        const unsigned o = (ax < kTabR && off < kTabR * kTabR) ? off : (unsigned)(kTabR * kTabR);
-        const float g = __ldg(table + ((unsigned)e.z + o));
+        const unsigned idx = __sad(cy64 + 8 * kTabW * j, e.y, ax);   // base + |dy| * kTabW + |dx|
+        // every pillar of the list meets the tile: |dx| <= r + 31, |dy| <= r + 8 R - 1 -- inside the table
+        const float g = __ldg(table + idx);
         best[j] = fmaxf(best[j], g);
         if (g > 0.f) last[j] = max(last[j], e.w);    // inside the window (see g_radar_tab)
       }
@@ -468,10 +468,8 @@ static int launch_radar_tiles(const RadarParams &p, const float *rcs, const int4
   const int tiles_x = ceil_div(p.nx, 32), tiles_y = ceil_div(p.ny, 8 * R);
   float *table = nullptr;
   RCB_CUDA_TRY(cudaGetSymbolAddress((void **)&table, g_radar_tab));
-  k_radar_tiles<R><<<(unsigned)(p.B * tiles_x * tiles_y), 256, 0, s>>>(p, rcs, rec, range, pillar_at, heatmap,
-                                                                      heatmap_feat, tiles_x, tiles_y, table,
-                                                                      point_features, features);
-  RCB_LAUNCH_CHECK();
+  RCB_CUDA_TRY(launch_pdl(k_radar_tiles<R>, (unsigned)(p.B * tiles_x * tiles_y), 256, 0, s, p, rcs, rec, range, pillar_at,
+                          heatmap, heatmap_feat, tiles_x, tiles_y, (const float *)table, point_features, features));
   return RCB_OK;
 }
 
