@@ -433,3 +433,20 @@ def test_channels_last_result_and_gradient_in_place():
     conv(rcb.voxel_pooling_v2(coor.cuda(), d2, f2, lo, iv, sz)).square().mean().backward()
     assert float((d.grad - d2.grad).abs().max()) <= 1e-4 * float(d2.grad.abs().max())
     assert float((f.grad - f2.grad).abs().max()) <= 1e-4 * float(f2.grad.abs().max())
+
+
+def test_forward_bits_do_not_depend_on_the_batch_size():
+    """The cell-stationary forward picks its CTA shape by the number of samples in the launch (1 / 2-4 /
+    more); every shape pools a cell with one warp in point order, so a sample pooled alone, in a batch of
+    3 and in a batch of 6 gives the same bits."""
+    import rcbevdet_b200 as rcb
+    from rcbevdet_b200 import rig
+    grid = rig.R50_GRID
+    coor, depth, feat = _case(B=6, depth_cfg=(1.0, 60.0, 1.0), input_size=(128, 352), C=80, aug=3, seed=5)
+    lo, iv, sz = rig.grid_tensors(grid)
+    with torch.no_grad():
+        full = rcb.voxel_pooling_v2(coor.cuda(), depth.cuda(), feat.cuda(), lo, iv, sz)
+        three = rcb.voxel_pooling_v2(coor[:3].cuda(), depth[:3].cuda(), feat[:3].cuda(), lo, iv, sz)
+        one = rcb.voxel_pooling_v2(coor[1:2].cuda(), depth[1:2].cuda(), feat[1:2].cuda(), lo, iv, sz)
+    assert torch.equal(full[:3], three) and torch.equal(full[1:2], one)
+    assert float(one.abs().max()) > 0
